@@ -1,0 +1,598 @@
+// C ABI of libmasp_b200 (include/masp_b200.h).  Host-side orchestration in
+// C++ above hand-written sm_100a kernels; no CPU compute path exists here:
+// every entry point needs mb200_init to have found a CUDA device.
+#include <algorithm>
+#include <map>
+#include <mutex>
+
+#include "prover.cuh"
+#include "synth.cuh"
+#include "misc.cuh"
+
+namespace mb {
+
+unsigned long long g_launches = 0;
+MsmProfile g_msm_profile;
+
+// ---------------------------------------------------------------------------
+// process state
+// ---------------------------------------------------------------------------
+struct NttCache {
+    NttDomain dom;
+    DevBuf gpow;  // g^i, Montgomery (standalone coset_fft)
+};
+struct State {
+    bool inited = false;
+    int device = 0;
+    cudaStream_t main = 0;
+    std::vector<ProveCtx> ctxs;
+    uint32_t chunk = 16;
+    std::map<unsigned, NttCache*> ntt;
+    MsmScratch msm;
+    std::mutex mu;
+    double last_batch_ms = 0;  // device time of the last prove call (CUDA events on the chunk streams)
+};
+static State g;
+
+static void require_init() {
+    if (!g.inited) fail(MB200_ESTATE, "mb200_init has not been called%s", "");
+}
+static void set_ctx_count(size_t n) {
+#ifndef MB200_EMU
+    for (auto& c : g.ctxs)
+        if (c.have_stream) cudaStreamDestroy(c.stream);
+#endif
+    g.ctxs.clear();
+    g.ctxs.resize(n);
+#ifndef MB200_EMU
+    for (auto& c : g.ctxs) {
+        MB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        c.have_stream = true;
+    }
+#endif
+}
+
+static uint32_t standalone_window(size_t n) {
+    uint32_t best = 4;
+    double best_cost = 1e300;
+    for (uint32_t c = 4; c <= 18; ++c) {
+        double nw = msm_nwin(c);
+        double cost = (double)n * nw + 4.0 * nw * (double)(1u << (c - 1));
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = c;
+        }
+    }
+    return env_u32("MB200_C_MSM", best);
+}
+
+template <class F>
+static void msm_on_device_bases(const Affine<F>* bases, const uint8_t* scalars_host, size_t n, XYZZ<F>* out_dev) {
+    if (n == 0) {
+        dev_memset(out_dev, 0, sizeof(XYZZ<F>), g.main);
+        return;
+    }
+    if (n >= (1ull << 31)) fail(MB200_EINVAL, "MSM of %s%ld bases is too large", "", (long)n);
+    DevBuf sel(n * 4), pool(n * 32), flag(4);
+    IotaArgs ia{n, sel.as<uint32_t>()};
+    launch_iota_kernel(ia, g.main);
+    copy_h2d(pool.p, scalars_host, n * 32, g.main);
+    dev_memset(flag.p, 0, 4, g.main);
+    ValidateArgs va{n, pool.as<Fr>(), n, n, flag.as<uint32_t>()};
+    launch_validate_scalars(va, g.main);
+    MsmClass k = msm_make_class(bases, sel.as<uint32_t>(), (uint32_t)n, standalone_window(n), false);
+    msm_run<F>(k, 1, pool.as<uint32_t>(), n, out_dev, g.msm, g.main);
+    uint32_t bad = 0;
+    copy_d2h(&bad, flag.p, 4, g.main);
+    stream_sync(g.main);
+    if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
+}
+
+static NttCache& ntt_cache(unsigned log_n) {
+    auto it = g.ntt.find(log_n);
+    if (it != g.ntt.end()) return *it->second;
+    NttCache* c = new NttCache();
+    c->dom.build(log_n, g.main);
+    size_t n = (size_t)1 << log_n;
+    c->gpow.alloc(n * sizeof(Fr));
+    PowArgs pa;
+    pa.nthreads = n;
+    pa.out = c->gpow.as<Fr>();
+    pa.base = fr_from_u64_host(7);
+    pa.scale = Fr::one();
+    launch_fr_powers(pa, g.main);
+    g.ntt[log_n] = c;
+    return *c;
+}
+
+static void check_scalars_dev(const Fr* base, size_t per_row, size_t row_stride, size_t nrows, uint32_t* flag,
+                              cudaStream_t s) {
+    ValidateArgs va{per_row * nrows, base, per_row, row_stride, flag};
+    launch_validate_scalars(va, s);
+}
+
+static int prove_impl(const Params& P, size_t n_proofs, size_t rows, const ProveInputs& in, uint8_t* proofs_out) {
+    require_init();
+    if (n_proofs == 0) return MB200_OK;
+    if (!in.a || !in.b || !in.c || !in.inputs || !in.aux || !in.r || !in.s || !proofs_out)
+        fail(MB200_EINVAL, "null buffer%s", "");
+    size_t m = 1;
+    while (m < rows) m <<= 1;
+    if (rows == 0 || m != P.m)
+        fail(MB200_EINVAL, "rows does not match the key's domain%s (key m = %ld)", "", (long)P.m);
+    uint8_t* staged = (uint8_t*)host_alloc_pinned(n_proofs * 192);
+    try {
+        size_t ci = 0;
+#ifndef MB200_EMU
+        // every chunk stream starts after `ev0`; the batch ends at the latest per-stream end event
+        cudaEvent_t ev0;
+        std::vector<cudaEvent_t> ev1(g.ctxs.size());
+        MB_CUDA(cudaEventCreate(&ev0));
+        for (auto& e : ev1) MB_CUDA(cudaEventCreate(&e));
+        MB_CUDA(cudaEventRecord(ev0, g.main));
+        for (auto& x : g.ctxs) MB_CUDA(cudaStreamWaitEvent(x.stream, ev0, 0));
+#endif
+        for (auto& x : g.ctxs) {
+            x.flag.ensure(4);
+            dev_memset(x.flag.p, 0, 4, x.stream);
+        }
+        for (size_t first = 0; first < n_proofs; first += g.chunk, ++ci) {
+            uint32_t count = (uint32_t)std::min<size_t>(g.chunk, n_proofs - first);
+            ProveCtx& x = g.ctxs[ci % g.ctxs.size()];
+            prove_chunk(P, x, in, first, count, rows, staged);
+            // canonical-scalar check on what was just staged (abc and aux..s of the pool)
+            check_scalars_dev(x.abc.as<Fr>(), (size_t)count * 3 * rows, 0, 1, x.flag.as<uint32_t>(), x.stream);
+            check_scalars_dev(x.pool.as<Fr>() + P.idx_aux, P.idx_one - P.idx_aux, P.pool_stride, count,
+                              x.flag.as<uint32_t>(), x.stream);
+        }
+        uint32_t bad = 0;
+#ifndef MB200_EMU
+        for (size_t i = 0; i < g.ctxs.size(); ++i) MB_CUDA(cudaEventRecord(ev1[i], g.ctxs[i].stream));
+#endif
+        for (auto& x : g.ctxs) {
+            uint32_t b = 0;
+            copy_d2h(&b, x.flag.p, 4, x.stream);
+            stream_sync(x.stream);
+            bad |= b;
+        }
+#ifndef MB200_EMU
+        g.last_batch_ms = 0;
+        for (auto& e : ev1) {
+            float ms = 0;
+            MB_CUDA(cudaEventElapsedTime(&ms, ev0, e));
+            if (ms > g.last_batch_ms) g.last_batch_ms = ms;
+            cudaEventDestroy(e);
+        }
+        cudaEventDestroy(ev0);
+#endif
+        if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
+        memcpy(proofs_out, staged, n_proofs * 192);
+    } catch (...) {
+        for (auto& x : g.ctxs) {
+#ifndef MB200_EMU
+            cudaStreamSynchronize(x.stream);
+#endif
+        }
+        host_free_pinned(staged);
+        throw;
+    }
+    host_free_pinned(staged);
+    return MB200_OK;
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+#define MB_API_BEGIN                          \
+    std::lock_guard<std::mutex> _lk(g.mu);    \
+    try {
+#define MB_API_END                            \
+    }                                         \
+    catch (const Exc& e) { return e.code; }   \
+    catch (const std::bad_alloc&) {           \
+        last_error().code = MB200_ENOMEM;     \
+        snprintf(last_error().msg, sizeof last_error().msg, "host allocation failed"); \
+        return MB200_ENOMEM;                  \
+    }                                         \
+    return MB200_OK;
+
+struct mb200_params {
+    Params* p;
+};
+
+extern "C" {
+
+int mb200_init(const int* device_ids, int n_devices) {
+    MB_API_BEGIN
+    if (g.inited) return MB200_OK;
+#ifndef MB200_EMU
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        fail(MB200_ECUDA, "no CUDA device: %s (this library has no CPU path)", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    int dev = 0;
+    if (device_ids && n_devices > 0) dev = device_ids[0];
+    else MB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= count) fail(MB200_EINVAL, "device id out of range%s (%ld)", "", (long)dev);
+    MB_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    MB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) fail(MB200_ECUDA, "device %s is not sm_100 (compute capability %ld.x)", prop.name, (long)prop.major);
+    g.device = dev;
+    MB_CUDA(cudaStreamCreateWithFlags(&g.main, cudaStreamNonBlocking));
+#else
+    (void)device_ids;
+    (void)n_devices;
+#endif
+    g.chunk = env_u32("MB200_CHUNK", 16);
+    set_ctx_count(env_u32("MB200_STREAMS", 2));
+    g.inited = true;
+    MB_API_END
+}
+
+int mb200_shutdown(void) {
+    MB_API_BEGIN
+    if (!g.inited) return MB200_OK;
+    for (auto& kv : g.ntt) delete kv.second;
+    g.ntt.clear();
+    set_ctx_count(0);
+    g.msm = MsmScratch();
+#ifndef MB200_EMU
+    cudaStreamDestroy(g.main);
+#endif
+    g.inited = false;
+    MB_API_END
+}
+
+int mb200_params_load(const uint8_t* bytes, size_t len, const uint8_t* a_aux_density, const uint8_t* b_input_density,
+                      const uint8_t* b_aux_density, mb200_params** out) {
+    MB_API_BEGIN
+    require_init();
+    if (!out) fail(MB200_EINVAL, "null out pointer%s", "");
+    *out = nullptr;
+    Params* p = params_load(bytes, len, a_aux_density, b_input_density, b_aux_density, g.main);
+    *out = new mb200_params{p};
+    MB_API_END
+}
+
+int mb200_params_info(const mb200_params* p, uint64_t info[10]) {
+    MB_API_BEGIN
+    if (!p || !p->p || !info) fail(MB200_EINVAL, "null argument%s", "");
+    const Params& P = *p->p;
+    info[0] = P.n_inputs; info[1] = P.n_aux; info[2] = P.h_len; info[3] = P.a_len; info[4] = P.b_len;
+    info[5] = P.m; info[6] = P.consumed; info[7] = P.table_bytes; info[8] = P.k_hl.c; info[9] = P.k_a.c;
+    MB_API_END
+}
+
+void mb200_params_free(mb200_params* p) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!p) return;
+#ifndef MB200_EMU
+    cudaDeviceSynchronize();
+#endif
+    delete p->p;
+    delete p;
+}
+
+size_t mb200_params_synth_size(uint32_t n_inputs, uint32_t h_len, uint32_t l_len, uint32_t a_len, uint32_t b_len) {
+    return params_synth_size(n_inputs, h_len, l_len, a_len, b_len);
+}
+
+int mb200_params_synthesize(uint64_t seed, uint32_t n_inputs, uint32_t h_len, uint32_t l_len, uint32_t a_len,
+                            uint32_t b_len, uint8_t* out, size_t out_len) {
+    MB_API_BEGIN
+    require_init();
+    size_t need = params_synth_size(n_inputs, h_len, l_len, a_len, b_len);
+    if (!out || out_len < need) fail(MB200_EINVAL, "output buffer too small%s (need %ld bytes)", "", (long)need);
+    DevBuf d(need);
+    params_synthesize(seed, n_inputs, h_len, l_len, a_len, b_len, d.as<uint8_t>(), g.main);
+    copy_d2h(out, d.p, need, g.main);
+    stream_sync(g.main);
+    MB_API_END
+}
+
+int mb200_synth_points(uint64_t seed, uint32_t stream, uint64_t start, size_t n, int group, uint8_t* out) {
+    MB_API_BEGIN
+    require_init();
+    if (!out || (group != 1 && group != 2)) fail(MB200_EINVAL, "bad argument%s", "");
+    size_t bytes = n * (group == 1 ? 96 : 192);
+    DevBuf d(bytes);
+    SynthArgs a;
+    a.nthreads = n;
+    a.key = stream_key(seed, stream);
+    a.start = start;
+    a.out = d.as<uint8_t>();
+    a.g1 = g1_generator_host();
+    a.g2 = g2_generator_host();
+    if (group == 1) launch_synth_g1(a, g.main);
+    else launch_synth_g2(a, g.main);
+    copy_d2h(out, d.p, bytes, g.main);
+    stream_sync(g.main);
+    MB_API_END
+}
+
+int mb200_prove_batch(const mb200_params* p, size_t n_proofs, size_t rows, const uint8_t* a_evals,
+                      const uint8_t* b_evals, const uint8_t* c_evals, const uint8_t* inputs, const uint8_t* aux,
+                      const uint8_t* r, const uint8_t* s, uint8_t* proofs_out) {
+    MB_API_BEGIN
+    if (!p || !p->p) fail(MB200_EINVAL, "null parameters%s", "");
+    ProveInputs in{a_evals, b_evals, c_evals, inputs, aux, r, s, false};
+    return prove_impl(*p->p, n_proofs, rows, in, proofs_out);
+    MB_API_END
+}
+
+int mb200_prove_batch_device(const mb200_params* p, size_t n_proofs, size_t rows, const void* a_evals,
+                             const void* b_evals, const void* c_evals, const void* inputs, const void* aux,
+                             const void* r, const void* s, uint8_t* proofs_out) {
+    MB_API_BEGIN
+    if (!p || !p->p) fail(MB200_EINVAL, "null parameters%s", "");
+    ProveInputs in{(const uint8_t*)a_evals, (const uint8_t*)b_evals, (const uint8_t*)c_evals, (const uint8_t*)inputs,
+                   (const uint8_t*)aux, (const uint8_t*)r, (const uint8_t*)s, true};
+    return prove_impl(*p->p, n_proofs, rows, in, proofs_out);
+    MB_API_END
+}
+
+int mb200_msm_g1(const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t out[96]) {
+    MB_API_BEGIN
+    require_init();
+    if ((n && (!bases || !scalars)) || !out) fail(MB200_EINVAL, "null buffer%s", "");
+    DevBuf raw(n * 96), pts(n * sizeof(G1Affine)), bad(4), res(sizeof(G1XYZZ)), enc(96);
+    copy_h2d(raw.p, bases, n * 96, g.main);
+    dev_memset(bad.p, 0, 4, g.main);
+    DecodeArgs da{n, raw.as<uint8_t>(), pts.p, bad.as<uint32_t>()};
+    launch_decode_g1(da, g.main);
+    uint32_t bad_h = 0;
+    copy_d2h(&bad_h, bad.p, 4, g.main);
+    stream_sync(g.main);
+    if (bad_h) fail(MB200_EPARSE, "malformed G1 encoding%s", "");
+    msm_on_device_bases<Fp>(pts.as<G1Affine>(), scalars, n, res.as<G1XYZZ>());
+    EncodeArgs ea{1, res.p, enc.as<uint8_t>()};
+    launch_encode_g1(ea, g.main);
+    copy_d2h(out, enc.p, 96, g.main);
+    stream_sync(g.main);
+    MB_API_END
+}
+
+int mb200_msm_g2(const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t out[192]) {
+    MB_API_BEGIN
+    require_init();
+    if ((n && (!bases || !scalars)) || !out) fail(MB200_EINVAL, "null buffer%s", "");
+    DevBuf raw(n * 192), pts(n * sizeof(G2Affine)), bad(4), res(sizeof(G2XYZZ)), enc(192);
+    copy_h2d(raw.p, bases, n * 192, g.main);
+    dev_memset(bad.p, 0, 4, g.main);
+    DecodeArgs da{n, raw.as<uint8_t>(), pts.p, bad.as<uint32_t>()};
+    launch_decode_g2(da, g.main);
+    uint32_t bad_h = 0;
+    copy_d2h(&bad_h, bad.p, 4, g.main);
+    stream_sync(g.main);
+    if (bad_h) fail(MB200_EPARSE, "malformed G2 encoding%s", "");
+    msm_on_device_bases<Fp2>(pts.as<G2Affine>(), scalars, n, res.as<G2XYZZ>());
+    EncodeArgs ea{1, res.p, enc.as<uint8_t>()};
+    launch_encode_g2(ea, g.main);
+    copy_d2h(out, enc.p, 192, g.main);
+    stream_sync(g.main);
+    MB_API_END
+}
+
+int mb200_g1_bases_upload(const uint8_t* bases, size_t n, void** dev_bases) {
+    MB_API_BEGIN
+    require_init();
+    if (!bases || !dev_bases) fail(MB200_EINVAL, "null buffer%s", "");
+    DevBuf raw(n * 96), bad(4);
+    void* pts = dev_alloc(n * sizeof(G1Affine));
+    copy_h2d(raw.p, bases, n * 96, g.main);
+    dev_memset(bad.p, 0, 4, g.main);
+    DecodeArgs da{n, raw.as<uint8_t>(), pts, bad.as<uint32_t>()};
+    launch_decode_g1(da, g.main);
+    uint32_t bad_h = 0;
+    copy_d2h(&bad_h, bad.p, 4, g.main);
+    stream_sync(g.main);
+    if (bad_h) {
+        dev_free(pts);
+        fail(MB200_EPARSE, "malformed G1 encoding%s", "");
+    }
+    *dev_bases = pts;
+    MB_API_END
+}
+
+int mb200_dev_free(void* p) {
+    MB_API_BEGIN
+    dev_free(p);
+    MB_API_END
+}
+
+int mb200_msm_g1_partial(const void* dev_bases, const uint8_t* scalars, size_t n, uint8_t out_partial[192]) {
+    MB_API_BEGIN
+    require_init();
+    if ((n && (!dev_bases || !scalars)) || !out_partial) fail(MB200_EINVAL, "null buffer%s", "");
+    DevBuf res(sizeof(G1XYZZ));
+    msm_on_device_bases<Fp>((const G1Affine*)dev_bases, scalars, n, res.as<G1XYZZ>());
+    copy_d2h(out_partial, res.p, sizeof(G1XYZZ), g.main);
+    stream_sync(g.main);
+    MB_API_END
+}
+
+int mb200_g1_sum_partials(const uint8_t* partials, size_t count, uint8_t out[96]) {
+    MB_API_BEGIN
+    require_init();
+    if ((count && !partials) || !out) fail(MB200_EINVAL, "null buffer%s", "");
+    DevBuf parts(count * sizeof(G1XYZZ)), enc(96);
+    copy_h2d(parts.p, partials, count * sizeof(G1XYZZ), g.main);
+    SumPartialsArgs sa{1, parts.as<G1XYZZ>(), count, enc.as<uint8_t>()};
+    launch_sum_partials(sa, g.main);
+    copy_d2h(out, enc.p, 96, g.main);
+    stream_sync(g.main);
+    MB_API_END
+}
+
+int mb200_ntt(uint8_t* data, unsigned log_n, int inverse, int coset) {
+    MB_API_BEGIN
+    require_init();
+    if (!data) fail(MB200_EINVAL, "null buffer%s", "");
+    NttCache& c = ntt_cache(log_n);
+    size_t n = (size_t)1 << log_n;
+    DevBuf d(n * 32), t0(n * 32), t1(n * 32), o(n * 32), flag(4);
+    copy_h2d(d.p, data, n * 32, g.main);
+    dev_memset(flag.p, 0, 4, g.main);
+    check_scalars_dev(d.as<Fr>(), n, 0, 1, flag.as<uint32_t>(), g.main);
+    NttPlan p;
+    p.inverse = inverse != 0;
+    if (!inverse && coset) p.in_scale = c.gpow.as<Fr>();
+    if (inverse) p.out_scale = coset ? c.dom.cos_inv.as<Fr>() : c.dom.minv_tab.as<Fr>();
+    ntt_run(c.dom, p, 1, d.as<Fr>(), n, o.as<Fr>(), n, t0.as<Fr>(), t1.as<Fr>(), g.main);
+    uint32_t bad = 0;
+    copy_d2h(&bad, flag.p, 4, g.main);
+    copy_d2h(data, o.p, n * 32, g.main);
+    stream_sync(g.main);
+    if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
+    MB_API_END
+}
+
+int mb200_h_coeffs(const uint8_t* a, const uint8_t* b, const uint8_t* c, size_t rows, uint8_t* out) {
+    MB_API_BEGIN
+    require_init();
+    if (!a || !b || !c || !out || rows < 2) fail(MB200_EINVAL, "bad argument (rows must be >= 2)%s", "");
+    unsigned log_n = 0;
+    while (((size_t)1 << log_n) < rows) log_n++;
+    NttCache& cache = ntt_cache(log_n);
+    size_t n = (size_t)1 << log_n;
+    DevBuf abc(3 * rows * 32), w0(3 * n * 32), w1(3 * n * 32), w2(3 * n * 32), w3(3 * n * 32), h(n * 32), flag(4);
+    copy_h2d(abc.as<uint8_t>(), a, rows * 32, g.main);
+    copy_h2d(abc.as<uint8_t>() + rows * 32, b, rows * 32, g.main);
+    copy_h2d(abc.as<uint8_t>() + 2 * rows * 32, c, rows * 32, g.main);
+    dev_memset(flag.p, 0, 4, g.main);
+    check_scalars_dev(abc.as<Fr>(), 3 * rows, 0, 1, flag.as<uint32_t>(), g.main);
+    h_pipeline(cache.dom, 1, (uint32_t)rows, abc.as<Fr>(), rows, h.as<Fr>(), n, w0.as<Fr>(), w1.as<Fr>(), w2.as<Fr>(),
+               w3.as<Fr>(), g.main);
+    uint32_t bad = 0;
+    copy_d2h(&bad, flag.p, 4, g.main);
+    copy_d2h(out, h.p, (n - 1) * 32, g.main);
+    stream_sync(g.main);
+    if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
+    MB_API_END
+}
+
+static void fr_mul_dev(const void* a, const void* b, size_t n, void* out) {
+    FrMulArgs fa{n, (const Fr*)a, (const Fr*)b, (Fr*)out};
+    launch_fr_mul_kernel(fa, g.main);
+}
+int mb200_fr_mul(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
+    MB_API_BEGIN
+    require_init();
+    if (n && (!a || !b || !out)) fail(MB200_EINVAL, "null buffer%s", "");
+    DevBuf da(n * 32), db(n * 32), dc(n * 32);
+    copy_h2d(da.p, a, n * 32, g.main);
+    copy_h2d(db.p, b, n * 32, g.main);
+    fr_mul_dev(da.p, db.p, n, dc.p);
+    copy_d2h(out, dc.p, n * 32, g.main);
+    stream_sync(g.main);
+    MB_API_END
+}
+int mb200_fr_mul_device(const void* a, const void* b, size_t n, void* out) {
+    MB_API_BEGIN
+    require_init();
+    if (n && (!a || !b || !out)) fail(MB200_EINVAL, "null buffer%s", "");
+    fr_mul_dev(a, b, n, out);
+    stream_sync(g.main);
+    MB_API_END
+}
+
+int mb200_set_option(const char* name, long value) {
+    MB_API_BEGIN
+    require_init();
+    if (!name) fail(MB200_EINVAL, "null name%s", "");
+    if (!strcmp(name, "chunk")) {
+        if (value < 1 || value > 4096) fail(MB200_EINVAL, "chunk out of range%s (%ld)", "", value);
+        g.chunk = (uint32_t)value;
+    } else if (!strcmp(name, "streams")) {
+        if (value < 1 || value > 8) fail(MB200_EINVAL, "streams out of range%s (%ld)", "", value);
+        set_ctx_count((size_t)value);
+    } else if (!strcmp(name, "profile")) {
+        g_msm_profile.enabled = value != 0;
+        g_msm_profile.acc_ms = 0;
+        g_msm_profile.acc_launches = 0;
+        g_msm_profile.acc_entries_bound = 0;
+    } else {
+        fail(MB200_EINVAL, "unknown option %s", name);
+    }
+    MB_API_END
+}
+
+int mb200_get_counter(const char* name, double* value) {
+    MB_API_BEGIN
+    if (!name || !value) fail(MB200_EINVAL, "null argument%s", "");
+    if (!strcmp(name, "launches")) *value = (double)g_launches;
+    else if (!strcmp(name, "acc_launches")) *value = (double)g_msm_profile.acc_launches;
+    else if (!strcmp(name, "acc_us")) *value = g_msm_profile.acc_ms * 1000.0;
+    else if (!strcmp(name, "acc_bytes")) *value = (double)g_msm_profile.acc_entries_bound;
+    else if (!strcmp(name, "last_batch_us")) *value = g.last_batch_ms * 1000.0;
+    else fail(MB200_EINVAL, "unknown counter %s", name);
+    MB_API_END
+}
+
+int mb200_selftest(void) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    try {
+        require_init();
+        uint32_t bad = 0;
+        DevBuf d(4);
+        dev_memset(d.p, 0, 4, g.main);
+        SelfTestArgs a;
+        a.nthreads = 4096;
+        a.mismatches = d.as<uint32_t>();
+        a.g1 = g1_generator_host();
+        a.g2 = g2_generator_host();
+        launch_selftest_kernel(a, g.main);
+        copy_d2h(&bad, d.p, 4, g.main);
+        stream_sync(g.main);
+        return (int)bad;
+    } catch (const Exc& e) {
+        return e.code;
+    }
+}
+
+int mb200_bench_fpmul(double* muls_per_second) {
+    MB_API_BEGIN
+    require_init();
+    if (!muls_per_second) fail(MB200_EINVAL, "null argument%s", "");
+#ifndef MB200_EMU
+    FpMulBenchArgs a;
+    a.nthreads = (size_t)148 * 2048 * 4;
+    a.iters = 512;
+    DevBuf sink(a.nthreads * sizeof(Fp));
+    a.sink = sink.as<Fp>();
+    launch_fpmul_bench(a, g.main);  // warm-up
+    cudaEvent_t e0, e1;
+    MB_CUDA(cudaEventCreate(&e0));
+    MB_CUDA(cudaEventCreate(&e1));
+    MB_CUDA(cudaEventRecord(e0, g.main));
+    launch_fpmul_bench(a, g.main);
+    MB_CUDA(cudaEventRecord(e1, g.main));
+    MB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    MB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *muls_per_second = (double)a.nthreads * a.iters * 4 / (ms * 1e-3);
+#else
+    *muls_per_second = 0;
+#endif
+    MB_API_END
+}
+
+const char* mb200_strerror(int code) {
+    switch (code) {
+        case MB200_OK: return "ok";
+        case MB200_EINVAL: return "invalid argument";
+        case MB200_EPARSE: return "malformed parameters";
+        case MB200_ECUDA: return "CUDA failure or no device";
+        case MB200_ENOMEM: return "out of memory";
+        case MB200_ESTATE: return "mb200_init has not been called";
+        case MB200_ESCALAR: return "scalar is not canonical";
+        default: return "unknown error";
+    }
+}
+const char* mb200_last_error(void) { return last_error().msg; }
+
+}  // extern "C"

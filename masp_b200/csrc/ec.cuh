@@ -1,0 +1,298 @@
+// Short-Weierstrass arithmetic for BLS12-381 G1 (over Fp) and G2 (over Fp2),
+// y^2 = x^3 + b with a = 0, in extended Jacobian "XYZZ" coordinates
+// (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2): the cheapest mixed addition (8M + 2S)
+// for bucket accumulation, where one operand is always an affine key point.
+//
+// Replaces the G1/G2 add/double/mixed-add the reference takes from nam-blstrs
+// (SURVEY.md §2 #3).  Every formula handles the exceptional inputs exactly
+// (identity, P + P, P + (-P)), so the result is the same group element the
+// reference computes for any input, not only for generic ones.
+#pragma once
+#include "field.cuh"
+
+namespace mb {
+
+// Affine point; the identity is encoded as x = y = 0 (not on either curve).
+template <class F>
+struct Affine {
+    F x, y;
+    MB_HD bool is_inf() const { return x.is_zero() && y.is_zero(); }
+    MB_HD static Affine inf() { return {F::zero(), F::zero()}; }
+};
+
+template <class F>
+struct XYZZ {
+    F x, y, zz, zzz;
+    MB_HD bool is_inf() const { return zz.is_zero(); }
+    MB_HD static XYZZ inf() { return {F::zero(), F::zero(), F::zero(), F::zero()}; }
+    MB_HD static XYZZ from_affine(const Affine<F>& p) {
+        if (p.is_inf()) return inf();
+        return {p.x, p.y, F::one(), F::one()};
+    }
+};
+
+template <class F>
+MB_COLD XYZZ<F> xyzz_dbl_cold(const XYZZ<F>& p);
+template <class F>
+MB_COLD XYZZ<F> xyzz_dbl_affine_cold(const Affine<F>& p);
+
+// 2 * (affine P)
+template <class F>
+MB_HD XYZZ<F> xyzz_dbl_affine(const Affine<F>& p) {
+    // U = 2Y, V = U^2, W = U V, S = X V, M = 3 X^2
+    if (p.is_inf() || p.y.is_zero()) return XYZZ<F>::inf();
+    F U = F::dbl(p.y);
+    F V = F::sqr(U);
+    F W = F::mul(U, V);
+    F S = F::mul(p.x, V);
+    F X2 = F::sqr(p.x);
+    F M = F::add(F::dbl(X2), X2);
+    XYZZ<F> r;
+    r.x = F::sub(F::sqr(M), F::dbl(S));
+    r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
+    r.zz = V;
+    r.zzz = W;
+    return r;
+}
+
+// 2 * P
+template <class F>
+MB_HD XYZZ<F> xyzz_dbl(const XYZZ<F>& p) {
+    if (p.is_inf() || p.y.is_zero()) return XYZZ<F>::inf();
+    F U = F::dbl(p.y);
+    F V = F::sqr(U);
+    F W = F::mul(U, V);
+    F S = F::mul(p.x, V);
+    F X2 = F::sqr(p.x);
+    F M = F::add(F::dbl(X2), X2);
+    XYZZ<F> r;
+    r.x = F::sub(F::sqr(M), F::dbl(S));
+    r.y = F::sub(F::mul(M, F::sub(S, r.x)), F::mul(W, p.y));
+    r.zz = F::mul(V, p.zz);
+    r.zzz = F::mul(W, p.zzz);
+    return r;
+}
+
+// acc += (affine q), q optionally negated
+template <class F>
+MB_HD void xyzz_madd(XYZZ<F>& acc, const Affine<F>& q_in, bool negate) {
+    if (q_in.is_inf()) return;
+    Affine<F> q = q_in;
+    if (negate) q.y = F::neg(q.y);
+    if (acc.is_inf()) {
+        acc.x = q.x;
+        acc.y = q.y;
+        acc.zz = F::one();
+        acc.zzz = F::one();
+        return;
+    }
+    F U2 = F::mul(q.x, acc.zz);
+    F S2 = F::mul(q.y, acc.zzz);
+    F P = F::sub(U2, acc.x);
+    F R = F::sub(S2, acc.y);
+    if (P.is_zero()) {
+        if (R.is_zero()) acc = xyzz_dbl_affine_cold(q);
+        else acc = XYZZ<F>::inf();
+        return;
+    }
+    F PP = F::sqr(P);
+    F PPP = F::mul(P, PP);
+    F Q = F::mul(acc.x, PP);
+    F X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
+    F Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(acc.y, PPP));
+    acc.x = X3;
+    acc.y = Y3;
+    acc.zz = F::mul(acc.zz, PP);
+    acc.zzz = F::mul(acc.zzz, PPP);
+}
+
+// acc += q
+template <class F>
+MB_HD void xyzz_add(XYZZ<F>& acc, const XYZZ<F>& q) {
+    if (q.is_inf()) return;
+    if (acc.is_inf()) {
+        acc = q;
+        return;
+    }
+    F U1 = F::mul(acc.x, q.zz);
+    F U2 = F::mul(q.x, acc.zz);
+    F S1 = F::mul(acc.y, q.zzz);
+    F S2 = F::mul(q.y, acc.zzz);
+    F P = F::sub(U2, U1);
+    F R = F::sub(S2, S1);
+    if (P.is_zero()) {
+        if (R.is_zero()) acc = xyzz_dbl_cold(acc);
+        else acc = XYZZ<F>::inf();
+        return;
+    }
+    F PP = F::sqr(P);
+    F PPP = F::mul(P, PP);
+    F Q = F::mul(U1, PP);
+    F X3 = F::sub(F::sub(F::sqr(R), PPP), F::dbl(Q));
+    F Y3 = F::sub(F::mul(R, F::sub(Q, X3)), F::mul(S1, PPP));
+    acc.x = X3;
+    acc.y = Y3;
+    acc.zz = F::mul(F::mul(acc.zz, q.zz), PP);
+    acc.zzz = F::mul(F::mul(acc.zzz, q.zzz), PPP);
+}
+
+// Out-of-line copies for everything off the bucket-accumulation hot loop:
+// one body per field instead of one per call site (keeps ptxas time and
+// instruction-cache footprint down; the call overhead is noise next to the
+// dozen multiplications inside).
+template <class F>
+MB_COLD void xyzz_add_cold(XYZZ<F>& acc, const XYZZ<F>& q) { xyzz_add(acc, q); }
+template <class F>
+MB_COLD void xyzz_madd_cold(XYZZ<F>& acc, const Affine<F>& q, bool negate) { xyzz_madd(acc, q, negate); }
+template <class F>
+MB_COLD XYZZ<F> xyzz_dbl_cold(const XYZZ<F>& p) { return xyzz_dbl(p); }
+template <class F>
+MB_COLD XYZZ<F> xyzz_dbl_affine_cold(const Affine<F>& p) { return xyzz_dbl_affine(p); }
+template <class F>
+MB_COLD F field_inv_cold(const F& a) { return F::inv(a); }
+
+// affine image: x = X / ZZ, y = Y / ZZZ via one inversion of ZZ * ZZZ
+template <class F>
+MB_COLD Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
+    if (p.is_inf()) return Affine<F>::inf();
+    F t = field_inv_cold(F::mul(p.zz, p.zzz));
+    F izz = F::mul(t, p.zzz);
+    F izzz = F::mul(t, p.zz);
+    return {F::mul(p.x, izz), F::mul(p.y, izzz)};
+}
+
+// k * P for a 256-bit plain little-endian scalar (8 limbs), MSB first
+template <class F>
+MB_COLD XYZZ<F> xyzz_mul(const XYZZ<F>& p, const uint32_t* k) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    MB_NOUNROLL
+    for (int i = 255; i >= 0; --i) {
+        acc = xyzz_dbl_cold(acc);
+        if ((k[i >> 5] >> (i & 31)) & 1) xyzz_add_cold(acc, p);
+    }
+    return acc;
+}
+template <class F>
+MB_COLD XYZZ<F> xyzz_mul_affine(const Affine<F>& p, const uint32_t* k) {
+    XYZZ<F> acc = XYZZ<F>::inf();
+    MB_NOUNROLL
+    for (int i = 255; i >= 0; --i) {
+        acc = xyzz_dbl_cold(acc);
+        if ((k[i >> 5] >> (i & 31)) & 1) xyzz_madd_cold(acc, p, false);
+    }
+    return acc;
+}
+
+typedef Affine<Fp> G1Affine;
+typedef Affine<Fp2> G2Affine;
+typedef XYZZ<Fp> G1XYZZ;
+typedef XYZZ<Fp2> G2XYZZ;
+
+// ---------------------------------------------------------------------------
+// wire encodings; plain-integer big-endian bytes
+// ---------------------------------------------------------------------------
+// 48 big-endian bytes -> limbs (plain integer, not reduced, not Montgomery)
+MB_HD void fp_limbs_from_be(const uint8_t* b, Fp& out) {
+    for (int i = 0; i < 12; ++i) {
+        const uint8_t* q = b + 4 * (11 - i);
+        out.v[i] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | (uint32_t)q[3];
+    }
+}
+MB_HD void fp_limbs_to_be(const Fp& a, uint8_t* b) {
+    for (int i = 0; i < 12; ++i) {
+        uint8_t* q = b + 4 * (11 - i);
+        q[0] = (uint8_t)(a.v[i] >> 24);
+        q[1] = (uint8_t)(a.v[i] >> 16);
+        q[2] = (uint8_t)(a.v[i] >> 8);
+        q[3] = (uint8_t)a.v[i];
+    }
+}
+
+// Uncompressed G1 (96 B).  Returns false when malformed: a flag bit other
+// than "infinity", non-zero bytes in an infinity encoding, or a coordinate
+// that is not canonical.  No curve / subgroup check: the reference reads
+// with checked = false (masp_proofs/src/lib.rs:336-341).
+MB_COLD bool g1_decode(const uint8_t* b, G1Affine& out) {
+    uint32_t flags = b[0] >> 5;
+    if (flags & 0x5) return false;
+    if (flags & 0x2) {
+        uint32_t o = b[0] & 0x1f;
+        for (int i = 1; i < 96; ++i) o |= b[i];
+        out = G1Affine::inf();
+        return o == 0;
+    }
+    Fp x, y;
+    fp_limbs_from_be(b, x);
+    fp_limbs_from_be(b + 48, y);
+    if (Fp::std_ge_mod(x) || Fp::std_ge_mod(y)) return false;
+    out.x = Fp::from_std(x);
+    out.y = Fp::from_std(y);
+    return true;
+}
+MB_COLD bool g2_decode(const uint8_t* b, G2Affine& out) {
+    uint32_t flags = b[0] >> 5;
+    if (flags & 0x5) return false;
+    if (flags & 0x2) {
+        uint32_t o = b[0] & 0x1f;
+        for (int i = 1; i < 192; ++i) o |= b[i];
+        out = G2Affine::inf();
+        return o == 0;
+    }
+    Fp xc1, xc0, yc1, yc0;
+    fp_limbs_from_be(b, xc1);
+    fp_limbs_from_be(b + 48, xc0);
+    fp_limbs_from_be(b + 96, yc1);
+    fp_limbs_from_be(b + 144, yc0);
+    if (Fp::std_ge_mod(xc1) || Fp::std_ge_mod(xc0) || Fp::std_ge_mod(yc1) || Fp::std_ge_mod(yc0)) return false;
+    out.x.c0 = Fp::from_std(xc0);
+    out.x.c1 = Fp::from_std(xc1);
+    out.y.c0 = Fp::from_std(yc0);
+    out.y.c1 = Fp::from_std(yc1);
+    return true;
+}
+MB_COLD void g1_encode(const G1Affine& p, uint8_t* b) {
+    if (p.is_inf()) {
+        for (int i = 0; i < 96; ++i) b[i] = 0;
+        b[0] = 0x40;
+        return;
+    }
+    fp_limbs_to_be(Fp::to_std(p.x), b);
+    fp_limbs_to_be(Fp::to_std(p.y), b + 48);
+}
+MB_COLD void g2_encode(const G2Affine& p, uint8_t* b) {
+    if (p.is_inf()) {
+        for (int i = 0; i < 192; ++i) b[i] = 0;
+        b[0] = 0x40;
+        return;
+    }
+    fp_limbs_to_be(Fp::to_std(p.x.c1), b);
+    fp_limbs_to_be(Fp::to_std(p.x.c0), b + 48);
+    fp_limbs_to_be(Fp::to_std(p.y.c1), b + 96);
+    fp_limbs_to_be(Fp::to_std(p.y.c0), b + 144);
+}
+// Compressed encodings: x with flag bits; sort flag iff y is the
+// lexicographically larger of {y, -y} (G2: compare c1 first, then c0).
+MB_COLD void g1_encode_compressed(const G1Affine& p, uint8_t* b) {
+    if (p.is_inf()) {
+        for (int i = 0; i < 48; ++i) b[i] = 0;
+        b[0] = 0xc0;
+        return;
+    }
+    fp_limbs_to_be(Fp::to_std(p.x), b);
+    b[0] |= 0x80;
+    if (Fp::std_gt_half(Fp::to_std(p.y))) b[0] |= 0x20;
+}
+MB_COLD void g2_encode_compressed(const G2Affine& p, uint8_t* b) {
+    if (p.is_inf()) {
+        for (int i = 0; i < 96; ++i) b[i] = 0;
+        b[0] = 0xc0;
+        return;
+    }
+    fp_limbs_to_be(Fp::to_std(p.x.c1), b);
+    fp_limbs_to_be(Fp::to_std(p.x.c0), b + 48);
+    b[0] |= 0x80;
+    bool larger = p.y.c1.is_zero() ? Fp::std_gt_half(Fp::to_std(p.y.c0)) : Fp::std_gt_half(Fp::to_std(p.y.c1));
+    if (larger) b[0] |= 0x20;
+}
+
+}  // namespace mb

@@ -1,0 +1,388 @@
+// Montgomery arithmetic over the BLS12-381 base field Fp (12 x 32-bit limbs)
+// and scalar field Fr (8 x 32-bit limbs), kept in registers.
+//
+// Replaces, for the proving path, the field layer the reference takes from
+// nam-blstrs / nam-blst (reference Cargo.lock:1385-1411).
+//
+// Multiplication is operand-scanning Montgomery with the partial products
+// split over two accumulators by limb parity ("even"/"odd" columns), so that
+// every 32x32->64 product (mad.lo.cc / madc.hi.cc pair on the IMAD pipe) joins
+// one unbroken carry chain; the two accumulators are one limb apart and swap
+// roles on every 32-bit shift of the reduction.
+#pragma once
+#include "rt.cuh"
+
+namespace mb {
+
+// ---------------------------------------------------------------------------
+// carry-chain primitives: PTX on the device, exact emulation on the host
+// ---------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+MB_D uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MB_D uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MB_D uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MB_D uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MB_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MB_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MB_D uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MB_D uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MB_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+MB_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+MB_D uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+MB_D uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+MB_D uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#else
+// The host build models CC.CF with one thread-local flag; each helper has the
+// exact semantics of the PTX instruction it stands for.
+inline uint32_t& cf() { static thread_local uint32_t f = 0; return f; }
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + cf(); cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + cf(); }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; cf() = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - cf(); cf() = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - cf(); }
+inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c; cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c + cf(); cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c; cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + cf(); cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)((((uint64_t)a * b) >> 32) + c + cf()); }
+#endif
+
+// ---------------------------------------------------------------------------
+// field parameters (little-endian 32-bit limbs)
+// ---------------------------------------------------------------------------
+struct FpCfg {
+    static constexpr int N = 12;
+    static constexpr uint32_t INV = 0xfffcfffdu;  // -p^{-1} mod 2^32
+    MB_HD static constexpr uint32_t mod(int i) {
+        constexpr uint32_t t[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                    0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+        return t[i];
+    }
+    MB_HD static constexpr uint32_t r1(int i) {  // 2^384 mod p
+        constexpr uint32_t t[12] = {0x0002fffdu, 0x76090000u, 0xc40c0002u, 0xebf4000bu, 0x53c758bau, 0x5f489857u,
+                                    0x70525745u, 0x77ce5853u, 0xa256ec6du, 0x5c071a97u, 0xfa80e493u, 0x15f65ec3u};
+        return t[i];
+    }
+    MB_HD static constexpr uint32_t r2(int i) {  // 2^768 mod p
+        constexpr uint32_t t[12] = {0x1c341746u, 0xf4df1f34u, 0x09d104f1u, 0x0a76e6a6u, 0x4c95b6d5u, 0x8de5476cu,
+                                    0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u};
+        return t[i];
+    }
+    MB_HD static constexpr uint32_t half(int i) {  // (p - 1) / 2
+        constexpr uint32_t t[12] = {0xffffd555u, 0xdcff7fffu, 0x58a9ffffu, 0x0f55ffffu, 0x7b587b12u, 0xb3986950u,
+                                    0x79c2895fu, 0xb23ba5c2u, 0x21a5d66bu, 0x258dd3dbu, 0x1cbff34du, 0x0d0088f5u};
+        return t[i];
+    }
+};
+struct FrCfg {
+    static constexpr int N = 8;
+    static constexpr uint32_t INV = 0xffffffffu;
+    MB_HD static constexpr uint32_t mod(int i) {
+        constexpr uint32_t t[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                   0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+        return t[i];
+    }
+    MB_HD static constexpr uint32_t r1(int i) {  // 2^256 mod r
+        constexpr uint32_t t[8] = {0xfffffffeu, 0x00000001u, 0x00034802u, 0x5884b7fau,
+                                   0xecbc4ff5u, 0x998c4fefu, 0xacc5056fu, 0x1824b159u};
+        return t[i];
+    }
+    MB_HD static constexpr uint32_t r2(int i) {  // 2^512 mod r
+        constexpr uint32_t t[8] = {0xf3f29c6du, 0xc999e990u, 0x87925c23u, 0x2b6cedcbu,
+                                   0x7254398fu, 0x05d31496u, 0x9f59ff11u, 0x0748d9d9u};
+        return t[i];
+    }
+    MB_HD static constexpr uint32_t half(int i) {
+        constexpr uint32_t t[8] = {0x80000000u, 0x7fffffffu, 0x7fff2dffu, 0xa9ded201u,
+                                   0x04d0ec02u, 0x199cec04u, 0x94cebea4u, 0x39f6d3a9u};
+        return t[i];
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Mont<Cfg>: an element in Montgomery form, fully reduced (< modulus)
+// ---------------------------------------------------------------------------
+template <class C>
+struct Mont {
+    static constexpr int N = C::N;
+    uint32_t v[N];
+
+    MB_HD static Mont zero() {
+        Mont r;
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) r.v[i] = 0;
+        return r;
+    }
+    MB_HD static Mont one() {
+        Mont r;
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) r.v[i] = C::r1(i);
+        return r;
+    }
+    MB_HD static Mont r2() {
+        Mont r;
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) r.v[i] = C::r2(i);
+        return r;
+    }
+    MB_HD bool is_zero() const {
+        uint32_t o = 0;
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) o |= v[i];
+        return o == 0;
+    }
+    MB_HD bool eq(const Mont& b) const {
+        uint32_t o = 0;
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) o |= v[i] ^ b.v[i];
+        return o == 0;
+    }
+
+    // r = a + b mod p
+    MB_HD static Mont add(const Mont& a, const Mont& b) {
+        Mont s, t;
+        s.v[0] = add_cc(a.v[0], b.v[0]);
+        MB_UNROLL
+        for (int i = 1; i < N - 1; ++i) s.v[i] = addc_cc(a.v[i], b.v[i]);
+        s.v[N - 1] = addc(a.v[N - 1], b.v[N - 1]);  // 2p < 2^(32N): no carry out
+        t.v[0] = sub_cc(s.v[0], C::mod(0));
+        MB_UNROLL
+        for (int i = 1; i < N; ++i) t.v[i] = subc_cc(s.v[i], C::mod(i));
+        uint32_t borrow = subc(0, 0);  // all ones iff s < p
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) s.v[i] = borrow ? s.v[i] : t.v[i];
+        return s;
+    }
+    // r = a - b mod p
+    MB_HD static Mont sub(const Mont& a, const Mont& b) {
+        Mont d;
+        d.v[0] = sub_cc(a.v[0], b.v[0]);
+        MB_UNROLL
+        for (int i = 1; i < N; ++i) d.v[i] = subc_cc(a.v[i], b.v[i]);
+        uint32_t m = subc(0, 0);  // all ones iff a < b
+        d.v[0] = add_cc(d.v[0], C::mod(0) & m);
+        MB_UNROLL
+        for (int i = 1; i < N - 1; ++i) d.v[i] = addc_cc(d.v[i], C::mod(i) & m);
+        d.v[N - 1] = addc(d.v[N - 1], C::mod(N - 1) & m);
+        return d;
+    }
+    MB_HD static Mont neg(const Mont& a) {
+        Mont d;
+        d.v[0] = sub_cc(C::mod(0), a.v[0]);
+        MB_UNROLL
+        for (int i = 1; i < N - 1; ++i) d.v[i] = subc_cc(C::mod(i), a.v[i]);
+        d.v[N - 1] = subc(C::mod(N - 1), a.v[N - 1]);
+        uint32_t nz = 0;
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) nz |= a.v[i];
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) d.v[i] = nz ? d.v[i] : 0u;
+        return d;
+    }
+    MB_HD static Mont dbl(const Mont& a) { return add(a, a); }
+
+    // one row of the parity-split accumulation: ev += x[even] * y, od += x[odd] * y
+    // (od first: its chain has no carry out; the ev chain's carry lands in od[N-1])
+    MB_HD static void row_acc(uint32_t* ev, uint32_t* od, const uint32_t* x, uint32_t y) {
+        od[0] = mad_lo_cc(x[1], y, od[0]);
+        od[1] = madc_hi_cc(x[1], y, od[1]);
+        MB_UNROLL
+        for (int j = 2; j < N; j += 2) {
+            od[j] = madc_lo_cc(x[j + 1], y, od[j]);
+            od[j + 1] = madc_hi_cc(x[j + 1], y, od[j + 1]);
+        }
+        ev[0] = mad_lo_cc(x[0], y, ev[0]);
+        ev[1] = madc_hi_cc(x[0], y, ev[1]);
+        MB_UNROLL
+        for (int j = 2; j < N; j += 2) {
+            ev[j] = madc_lo_cc(x[j], y, ev[j]);
+            ev[j + 1] = madc_hi_cc(x[j], y, ev[j + 1]);
+        }
+        od[N - 1] = addc(od[N - 1], 0);
+    }
+    // Montgomery step on the current row: make ev[0] vanish
+    MB_HD static void row_redc(uint32_t* ev, uint32_t* od) {
+        uint32_t m = mul_lo(ev[0], C::INV);
+        uint32_t p[N];
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) p[i] = C::mod(i);
+        row_acc(ev, od, p, m);
+    }
+    // Shift the pair right by one limb and add x * y: `ev` (the old odd
+    // accumulator) becomes the even one; `od` (the old even one, whose limb 0
+    // is now zero) slides down two limbs and becomes the odd one.
+    MB_HD static void row_shift_acc(uint32_t* ev, uint32_t* od, const uint32_t* x, uint32_t y) {
+        ev[0] = add_cc(ev[0], od[1]);
+        MB_UNROLL
+        for (int j = 0; j < N - 2; j += 2) {
+            od[j] = madc_lo_cc(x[j + 1], y, od[j + 2]);
+            od[j + 1] = madc_hi_cc(x[j + 1], y, od[j + 3]);
+        }
+        od[N - 2] = madc_lo_cc(x[N - 1], y, 0);
+        od[N - 1] = madc_hi(x[N - 1], y, 0);
+        ev[0] = mad_lo_cc(x[0], y, ev[0]);
+        ev[1] = madc_hi_cc(x[0], y, ev[1]);
+        MB_UNROLL
+        for (int j = 2; j < N; j += 2) {
+            ev[j] = madc_lo_cc(x[j], y, ev[j]);
+            ev[j + 1] = madc_hi_cc(x[j], y, ev[j + 1]);
+        }
+        od[N - 1] = addc(od[N - 1], 0);
+    }
+
+    // r = a * b * 2^(-32N) mod p
+    MB_HD static Mont mul(const Mont& a, const Mont& b) {
+        uint32_t ev[N], od[N];
+        // first row: plain products
+        MB_UNROLL
+        for (int j = 0; j < N; j += 2) {
+            ev[j] = mul_lo(a.v[j], b.v[0]);
+            ev[j + 1] = mul_hi(a.v[j], b.v[0]);
+            od[j] = mul_lo(a.v[j + 1], b.v[0]);
+            od[j + 1] = mul_hi(a.v[j + 1], b.v[0]);
+        }
+        row_redc(ev, od);
+        MB_UNROLL
+        for (int i = 1; i < N; i += 2) {
+            row_shift_acc(od, ev, a.v, b.v[i]);
+            row_redc(od, ev);
+            if (i + 1 < N) {
+                row_shift_acc(ev, od, a.v, b.v[i + 1]);
+                row_redc(ev, od);
+            }
+        }
+        // N is even: `od` ended as the even accumulator with od[0] == 0.
+        // result = (od >> 32) + ev
+        Mont s, t;
+        s.v[0] = add_cc(ev[0], od[1]);
+        MB_UNROLL
+        for (int i = 1; i < N - 1; ++i) s.v[i] = addc_cc(ev[i], od[i + 1]);
+        s.v[N - 1] = addc(ev[N - 1], 0);
+        // s < 2p: one conditional subtraction
+        t.v[0] = sub_cc(s.v[0], C::mod(0));
+        MB_UNROLL
+        for (int i = 1; i < N; ++i) t.v[i] = subc_cc(s.v[i], C::mod(i));
+        uint32_t borrow = subc(0, 0);
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) s.v[i] = borrow ? s.v[i] : t.v[i];
+        return s;
+    }
+    MB_HD static Mont sqr(const Mont& a) { return mul(a, a); }
+
+    // reference multiplication with 64-bit temporaries (self-test only)
+    MB_HD static Mont mul_portable(const Mont& a, const Mont& b) {
+        uint32_t t[N + 2];
+        for (int i = 0; i < N + 2; ++i) t[i] = 0;
+        for (int i = 0; i < N; ++i) {
+            uint64_t c = 0;
+            for (int j = 0; j < N; ++j) {
+                c += (uint64_t)a.v[j] * b.v[i] + t[j];
+                t[j] = (uint32_t)c;
+                c >>= 32;
+            }
+            c += t[N];
+            t[N] = (uint32_t)c;
+            t[N + 1] = (uint32_t)(c >> 32);
+            uint32_t m = t[0] * C::INV;
+            c = (uint64_t)m * C::mod(0) + t[0];
+            c >>= 32;
+            for (int j = 1; j < N; ++j) {
+                c += (uint64_t)m * C::mod(j) + t[j];
+                t[j - 1] = (uint32_t)c;
+                c >>= 32;
+            }
+            c += t[N];
+            t[N - 1] = (uint32_t)c;
+            t[N] = t[N + 1] + (uint32_t)(c >> 32);
+        }
+        // conditional subtract
+        uint32_t d[N];
+        uint64_t br = 0;
+        for (int i = 0; i < N; ++i) {
+            uint64_t x = (uint64_t)t[i] - C::mod(i) - br;
+            d[i] = (uint32_t)x;
+            br = (x >> 63) & 1;
+        }
+        Mont r;
+        bool ge = t[N] != 0 || br == 0;
+        for (int i = 0; i < N; ++i) r.v[i] = ge ? d[i] : t[i];
+        return r;
+    }
+
+    // plain integer (already < modulus) <-> Montgomery form
+    MB_HD static Mont from_std(const Mont& a) { return mul(a, r2()); }
+    MB_HD static Mont to_std(const Mont& a) {
+        Mont o = zero();
+        o.v[0] = 1;
+        return mul(a, o);
+    }
+    // a >= modulus ? (plain integers)
+    MB_HD static bool std_ge_mod(const Mont& a) {
+        sub_cc(a.v[0], C::mod(0));
+        MB_UNROLL
+        for (int i = 1; i < N; ++i) subc_cc(a.v[i], C::mod(i));
+        return subc(0, 0) == 0;
+    }
+    // plain integer a > (p-1)/2 ?
+    MB_HD static bool std_gt_half(const Mont& a) {
+        sub_cc(C::half(0), a.v[0]);
+        MB_UNROLL
+        for (int i = 1; i < N; ++i) subc_cc(C::half(i), a.v[i]);
+        return subc(0, 0) != 0;
+    }
+
+    // a^(p-2) by square-and-multiply over the bits of p - 2
+    MB_HD static Mont inv(const Mont& a) {
+        uint32_t e[N];
+        uint32_t borrow = 2;
+        for (int i = 0; i < N; ++i) {
+            uint32_t m = C::mod(i);
+            e[i] = m - borrow;
+            borrow = m < borrow ? 1u : 0u;
+        }
+        Mont r = one();
+        MB_NOUNROLL
+        for (int i = 32 * N - 1; i >= 0; --i) {
+            r = sqr(r);
+            if ((e[i >> 5] >> (i & 31)) & 1) r = mul(r, a);
+        }
+        return r;
+    }
+};
+
+typedef Mont<FpCfg> Fp;
+typedef Mont<FrCfg> Fr;
+
+// ---------------------------------------------------------------------------
+// Fp2 = Fp[u] / (u^2 + 1)
+// ---------------------------------------------------------------------------
+struct Fp2 {
+    Fp c0, c1;
+    MB_HD static Fp2 zero() { return {Fp::zero(), Fp::zero()}; }
+    MB_HD static Fp2 one() { return {Fp::one(), Fp::zero()}; }
+    MB_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    MB_HD bool eq(const Fp2& b) const { return c0.eq(b.c0) && c1.eq(b.c1); }
+    MB_HD static Fp2 add(const Fp2& a, const Fp2& b) { return {Fp::add(a.c0, b.c0), Fp::add(a.c1, b.c1)}; }
+    MB_HD static Fp2 sub(const Fp2& a, const Fp2& b) { return {Fp::sub(a.c0, b.c0), Fp::sub(a.c1, b.c1)}; }
+    MB_HD static Fp2 neg(const Fp2& a) { return {Fp::neg(a.c0), Fp::neg(a.c1)}; }
+    MB_HD static Fp2 dbl(const Fp2& a) { return {Fp::dbl(a.c0), Fp::dbl(a.c1)}; }
+    MB_HD static Fp2 mul(const Fp2& a, const Fp2& b) {
+        Fp t0 = Fp::mul(a.c0, b.c0);
+        Fp t1 = Fp::mul(a.c1, b.c1);
+        Fp t2 = Fp::mul(Fp::add(a.c0, a.c1), Fp::add(b.c0, b.c1));
+        return {Fp::sub(t0, t1), Fp::sub(Fp::sub(t2, t0), t1)};
+    }
+    MB_HD static Fp2 sqr(const Fp2& a) {
+        Fp t = Fp::mul(a.c0, a.c1);
+        return {Fp::mul(Fp::add(a.c0, a.c1), Fp::sub(a.c0, a.c1)), Fp::dbl(t)};
+    }
+    MB_HD static Fp2 inv(const Fp2& a) {
+        Fp t = Fp::inv(Fp::add(Fp::sqr(a.c0), Fp::sqr(a.c1)));
+        return {Fp::mul(a.c0, t), Fp::neg(Fp::mul(a.c1, t))};
+    }
+};
+
+}  // namespace mb

@@ -1,0 +1,3 @@
+// Kernel definitions of group MISC (see rt.cuh: one translation unit per group).
+#define MB_DEFINE_MISC
+#include "misc.cuh"

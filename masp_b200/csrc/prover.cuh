@@ -1,0 +1,435 @@
+// Device-resident proving key and the batched Groth16 prover.
+//
+// Drop-in for the work bellman::groth16::create_proof does after synthesis
+// (Appendix A), behind the reference call sites
+// masp_proofs/src/sapling/prover.rs:116-117 (Spend), 201-202 (Output),
+// 251-252 (Convert), with the key parsed exactly as
+// Parameters::<Bls12>::read(reader, false) does (masp_proofs/src/lib.rs:336-341).
+//
+// Per proof, four bucket MSMs over precomputed window tables:
+//   HL  = sum h_i H_i + sum aux_i L_i                       (G1, joins C)
+//   A   = sum_inputs + sum_dense-aux A_i  + r*delta1 + alpha1   = proof.A
+//   B1  = sum B1_i                         + beta1
+//   B2  = sum B2_i + s*delta2 + beta2                            = proof.B
+//   C   = s*A + r*B1 + HL
+// (delta, alpha, beta ride along as extra bases of the A / B tables, so the
+// only variable-base scalar multiplications left are the two in C.)
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace mb {
+
+
+// ---------------------------------------------------------------------------
+// kernels: ingest, table precompute, assembly
+// ---------------------------------------------------------------------------
+struct DecodeArgs {
+    size_t nthreads;
+    const uint8_t* src;   // nthreads encodings, 96 (G1) or 192 (G2) bytes each
+    void* dst;            // Affine<F>[nthreads]
+    uint32_t* bad;        // set to 1 on a malformed encoding
+};
+MB_HD void decode_g1_body(const DecodeArgs& a, size_t tid) {
+    G1Affine p;
+    if (!g1_decode(a.src + 96 * tid, p)) {
+        *a.bad = 1;
+        p = G1Affine::inf();
+    }
+    ((G1Affine*)a.dst)[tid] = p;
+}
+MB_HD void decode_g2_body(const DecodeArgs& a, size_t tid) {
+    G2Affine p;
+    if (!g2_decode(a.src + 192 * tid, p)) {
+        *a.bad = 1;
+        p = G2Affine::inf();
+    }
+    ((G2Affine*)a.dst)[tid] = p;
+}
+MB_K_G1(decode_g1, DecodeArgs, decode_g1_body, 128)
+MB_K_G2(decode_g2, DecodeArgs, decode_g2_body, 64)
+
+// table[w * n + k] = affine(2^(c w) * base_k), w < nwin
+template <class F>
+struct TableArgs {
+    size_t nthreads;  // n bases
+    const Affine<F>* bases;
+    Affine<F>* table;
+    uint32_t c, nwin;
+};
+template <class F>
+MB_HD void table_body(const TableArgs<F>& a, size_t tid) {
+    Affine<F> p = a.bases[tid];
+    a.table[tid] = p;
+    MB_NOUNROLL
+    for (uint32_t w = 1; w < a.nwin; ++w) {
+        XYZZ<F> j = xyzz_dbl_affine_cold(p);
+        MB_NOUNROLL
+        for (uint32_t d = 1; d < a.c; ++d) j = xyzz_dbl_cold(j);
+        p = xyzz_to_affine(j);
+        a.table[(size_t)w * a.nthreads + tid] = p;
+    }
+}
+MB_HD void table_g1_body(const TableArgs<Fp>& a, size_t tid) { table_body<Fp>(a, tid); }
+MB_HD void table_g2_body(const TableArgs<Fp2>& a, size_t tid) { table_body<Fp2>(a, tid); }
+MB_K_G1(build_table_g1, TableArgs<Fp>, table_g1_body, 128)
+MB_K_G2(build_table_g2, TableArgs<Fp2>, table_g2_body, 64)
+
+struct FillOneArgs {
+    size_t nthreads;  // proofs
+    uint32_t* pool;
+    size_t pool_stride;
+    size_t one_index;
+};
+MB_HD void fill_one_body(const FillOneArgs& a, size_t tid) {
+    uint32_t* p = a.pool + (tid * a.pool_stride + a.one_index) * 8;
+    p[0] = 1;
+    for (int i = 1; i < 8; ++i) p[i] = 0;
+}
+MB_K_G1(pool_fill_one, FillOneArgs, fill_one_body, 64)
+
+// s * A and r * B1 (two threads per proof)
+struct CmulArgs {
+    size_t nthreads;  // 2 * proofs
+    const G1XYZZ* a_res;
+    const G1XYZZ* b1_res;
+    const uint32_t* pool;
+    size_t pool_stride, r_index, s_index;
+    G1XYZZ* out;  // [proofs][2]
+};
+MB_HD void cmul_body(const CmulArgs& a, size_t tid) {
+    size_t proof = tid >> 1;
+    const uint32_t* base = a.pool + proof * a.pool_stride * 8;
+    if (tid & 1) a.out[tid] = xyzz_mul(a.b1_res[proof], base + a.r_index * 8);
+    else a.out[tid] = xyzz_mul(a.a_res[proof], base + a.s_index * 8);
+}
+MB_K_G1(proof_cmul, CmulArgs, cmul_body, 32)
+
+// affine + compressed encoding of the three proof points (three threads per proof)
+struct FinishArgs {
+    size_t nthreads;  // 3 * proofs
+    const G1XYZZ* a_res;
+    const G2XYZZ* b2_res;
+    const G1XYZZ* hl_res;
+    const G1XYZZ* cmul;  // [proofs][2]
+    uint8_t* proofs;     // 192 bytes each
+};
+MB_HD void finish_body(const FinishArgs& a, size_t tid) {
+    size_t proof = tid / 3;
+    uint32_t which = (uint32_t)(tid - proof * 3);
+    uint8_t* out = a.proofs + 192 * proof;
+    if (which == 0) {
+        g1_encode_compressed(xyzz_to_affine(a.a_res[proof]), out);
+    } else if (which == 1) {
+        g2_encode_compressed(xyzz_to_affine(a.b2_res[proof]), out + 48);
+    } else {
+        G1XYZZ c = a.hl_res[proof];
+        xyzz_add_cold(c, a.cmul[2 * proof]);
+        xyzz_add_cold(c, a.cmul[2 * proof + 1]);
+        g1_encode_compressed(xyzz_to_affine(c), out + 144);
+    }
+}
+MB_K_G2(proof_finish, FinishArgs, finish_body, 32)
+
+// uncompressed encoding of MSM results (standalone API)
+struct EncodeArgs {
+    size_t nthreads;
+    const void* pts;  // XYZZ<F>
+    uint8_t* out;
+};
+MB_HD void encode_g1_body(const EncodeArgs& a, size_t tid) {
+    g1_encode(xyzz_to_affine(((const G1XYZZ*)a.pts)[tid]), a.out + 96 * tid);
+}
+MB_HD void encode_g2_body(const EncodeArgs& a, size_t tid) {
+    g2_encode(xyzz_to_affine(((const G2XYZZ*)a.pts)[tid]), a.out + 192 * tid);
+}
+MB_K_G1(encode_g1, EncodeArgs, encode_g1_body, 32)
+MB_K_G2(encode_g2, EncodeArgs, encode_g2_body, 32)
+
+// ---------------------------------------------------------------------------
+// window-size heuristic: minimise bucket additions + reduction additions
+// ---------------------------------------------------------------------------
+inline uint32_t choose_window(double n_full_width, uint32_t cmax = 16) {
+    uint32_t best = 4;
+    double best_cost = 1e300;
+    for (uint32_t c = 4; c <= cmax; ++c) {
+        double cost = n_full_width * msm_nwin(c) + 4.0 * (double)(1u << (c - 1));
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = c;
+        }
+    }
+    return best;
+}
+inline uint32_t env_u32(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return (uint32_t)strtoul(v, nullptr, 10);
+}
+
+// ---------------------------------------------------------------------------
+// the key
+// ---------------------------------------------------------------------------
+struct Params {
+    uint32_t n_inputs = 0, n_aux = 0, h_len = 0, a_len = 0, b_len = 0, n_b_inputs = 0;
+    uint32_t log_m = 0, m = 0;
+    size_t consumed = 0;  // bytes of the Parameters encoding (the MPC transcript follows in real files)
+    // scalar pool layout (indices in scalars)
+    size_t pool_stride = 0, idx_aux = 0, idx_inputs = 0, idx_r = 0, idx_s = 0, idx_one = 0;
+    DevBuf t_hl, t_a, t_b1, t_b2;          // window tables
+    DevBuf sel_hl, sel_a, sel_b1, sel_b2;  // base -> pool index
+    MsmClass k_hl, k_a, k_b1, k_b2;
+    NttDomain dom;
+    std::vector<uint8_t> vk_bytes;  // the VerifyingKey prefix, verbatim
+    size_t table_bytes = 0;
+};
+
+static inline bool bm_bit(const uint8_t* bm, size_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
+static inline uint32_t be32(const uint8_t* p) {
+    return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3];
+}
+
+template <class F>
+inline void launch_table(const TableArgs<F>& a, cudaStream_t s);
+template <>
+inline void launch_table<Fp>(const TableArgs<Fp>& a, cudaStream_t s) { launch_build_table_g1(a, s); }
+template <>
+inline void launch_table<Fp2>(const TableArgs<Fp2>& a, cudaStream_t s) { launch_build_table_g2(a, s); }
+
+template <class F>
+inline MsmClass build_class(DevBuf& table, const DevBuf& bases, const DevBuf& sel, uint32_t n, uint32_t c,
+                            cudaStream_t s) {
+    uint32_t nwin = msm_nwin(c);
+    table.alloc((size_t)n * nwin * sizeof(Affine<F>));
+    TableArgs<F> ta;
+    ta.nthreads = n;
+    ta.bases = bases.as<Affine<F>>();
+    ta.table = table.as<Affine<F>>();
+    ta.c = c;
+    ta.nwin = nwin;
+    launch_table<F>(ta, s);
+    return msm_make_class(table.p, sel.as<uint32_t>(), n, c, true);
+}
+
+// Parameters::read(reader, checked = false) + densities -> device key.
+inline Params* params_load(const uint8_t* buf, size_t len, const uint8_t* a_aux_density,
+                           const uint8_t* b_input_density, const uint8_t* b_aux_density, cudaStream_t s) {
+    const size_t VK_FIXED = 3 * 96 + 3 * 192;
+    if (!buf || len < VK_FIXED + 4) fail(MB200_EPARSE, "parameters truncated (%s%ld bytes)", "", (long)len);
+    size_t pos = VK_FIXED;
+    auto need = [&](size_t n) {
+        if (n > len - pos) fail(MB200_EPARSE, "parameters truncated at byte %s%ld", "", (long)pos);
+    };
+    auto vec = [&](size_t elem, uint32_t& count, size_t& off) {
+        need(4);
+        count = be32(buf + pos);
+        pos += 4;
+        if ((size_t)count > (len - pos) / elem) fail(MB200_EPARSE, "parameters truncated at byte %s%ld", "", (long)pos);
+        off = pos;
+        pos += (size_t)count * elem;
+    };
+    uint32_t n_ic, n_h, n_l, n_a, n_b1, n_b2;
+    size_t o_ic, o_h, o_l, o_a, o_b1, o_b2;
+    vec(96, n_ic, o_ic);
+    size_t vk_end = pos;
+    vec(96, n_h, o_h);
+    vec(96, n_l, o_l);
+    vec(96, n_a, o_a);
+    vec(96, n_b1, o_b1);
+    vec(192, n_b2, o_b2);
+
+    std::unique_ptr<Params> P(new Params());
+    P->consumed = pos;
+    P->vk_bytes.assign(buf, buf + vk_end);
+    P->n_inputs = n_ic;
+    P->n_aux = n_l;
+    P->h_len = n_h;
+    P->a_len = n_a;
+    P->b_len = n_b1;
+    if (n_ic == 0) fail(MB200_EPARSE, "verifying key has no IC elements%s", "");
+    if (n_b2 != n_b1) fail(MB200_EPARSE, "b_g1 / b_g2 lengths differ%s (%ld)", "", (long)n_b2);
+    uint32_t m = n_h + 1;
+    if (m < 2 || (m & (m - 1))) fail(MB200_EPARSE, "h query length + 1 is not a power of two%s (%ld)", "", (long)n_h);
+    P->m = m;
+    while ((1u << P->log_m) < m) P->log_m++;
+
+    // density walk (Appendix A "MSMs"): k-th dense variable <-> k-th base
+    std::vector<uint32_t> a_sel, b_in_sel, b_sel;
+    for (uint32_t i = 0; i < n_l; ++i) {
+        if (!a_aux_density || bm_bit(a_aux_density, i)) a_sel.push_back(i);
+        if (!b_aux_density || bm_bit(b_aux_density, i)) b_sel.push_back(i);
+    }
+    for (uint32_t i = 0; i < n_ic; ++i)
+        if (!b_input_density || bm_bit(b_input_density, i)) b_in_sel.push_back(i);
+    if (n_a != n_ic + a_sel.size())
+        fail(MB200_EINVAL, "a query length does not match a_aux_density%s (%ld bases)", "", (long)n_a);
+    if (n_b1 != b_in_sel.size() + b_sel.size())
+        fail(MB200_EINVAL, "b query length does not match the b densities%s (%ld bases)", "", (long)n_b1);
+    P->n_b_inputs = (uint32_t)b_in_sel.size();
+
+    P->idx_aux = m;
+    P->idx_inputs = (size_t)m + n_l;
+    P->idx_r = P->idx_inputs + n_ic;
+    P->idx_s = P->idx_r + 1;
+    P->idx_one = P->idx_s + 1;
+    P->pool_stride = P->idx_one + 1;
+
+    // base -> pool index maps
+    std::vector<uint32_t> s_hl, s_a, s_b1, s_b2;
+    for (uint32_t i = 0; i < n_h; ++i) s_hl.push_back(i);
+    for (uint32_t i = 0; i < n_l; ++i) s_hl.push_back((uint32_t)P->idx_aux + i);
+    for (uint32_t i = 0; i < n_ic; ++i) s_a.push_back((uint32_t)P->idx_inputs + i);
+    for (uint32_t v : a_sel) s_a.push_back((uint32_t)P->idx_aux + v);
+    s_a.push_back((uint32_t)P->idx_r);    // delta_g1
+    s_a.push_back((uint32_t)P->idx_one);  // alpha_g1
+    for (uint32_t v : b_in_sel) s_b1.push_back((uint32_t)P->idx_inputs + v);
+    for (uint32_t v : b_sel) s_b1.push_back((uint32_t)P->idx_aux + v);
+    s_b2 = s_b1;
+    s_b1.push_back((uint32_t)P->idx_one);  // beta_g1
+    s_b2.push_back((uint32_t)P->idx_s);    // delta_g2
+    s_b2.push_back((uint32_t)P->idx_one);  // beta_g2
+    auto upload = [&](DevBuf& d, const std::vector<uint32_t>& v) {
+        d.alloc(v.size() * 4);
+        copy_h2d(d.p, v.data(), v.size() * 4, s);
+    };
+    upload(P->sel_hl, s_hl);
+    upload(P->sel_a, s_a);
+    upload(P->sel_b1, s_b1);
+    upload(P->sel_b2, s_b2);
+
+    // raw bytes -> Montgomery affine bases
+    DevBuf raw(pos), bad(4);
+    copy_h2d(raw.p, buf, pos, s);
+    dev_memset(bad.p, 0, 4, s);
+    const uint8_t* rb = raw.as<uint8_t>();
+    DevBuf b_hl((size_t)(n_h + n_l) * sizeof(G1Affine)), b_a((size_t)(n_a + 2) * sizeof(G1Affine)),
+        b_b1((size_t)(n_b1 + 1) * sizeof(G1Affine)), b_b2((size_t)(n_b2 + 2) * sizeof(G2Affine));
+    auto dec1 = [&](size_t off, uint32_t n, G1Affine* dst) {
+        DecodeArgs a{n, rb + off, dst, bad.as<uint32_t>()};
+        launch_decode_g1(a, s);
+    };
+    auto dec2 = [&](size_t off, uint32_t n, G2Affine* dst) {
+        DecodeArgs a{n, rb + off, dst, bad.as<uint32_t>()};
+        launch_decode_g2(a, s);
+    };
+    // VerifyingKey: alpha_g1 0, beta_g1 96, beta_g2 192, gamma_g2 384, delta_g1 576, delta_g2 672
+    dec1(o_h, n_h, b_hl.as<G1Affine>());
+    dec1(o_l, n_l, b_hl.as<G1Affine>() + n_h);
+    dec1(o_a, n_a, b_a.as<G1Affine>());
+    dec1(576, 1, b_a.as<G1Affine>() + n_a);
+    dec1(0, 1, b_a.as<G1Affine>() + n_a + 1);
+    dec1(o_b1, n_b1, b_b1.as<G1Affine>());
+    dec1(96, 1, b_b1.as<G1Affine>() + n_b1);
+    dec2(o_b2, n_b2, b_b2.as<G2Affine>());
+    dec2(672, 1, b_b2.as<G2Affine>() + n_b2);
+    dec2(192, 1, b_b2.as<G2Affine>() + n_b2 + 1);
+    // the remaining vk points are only checked for well-formedness
+    DevBuf scratch((size_t)(n_ic + 1) * sizeof(G2Affine));
+    dec2(384, 1, scratch.as<G2Affine>());
+    dec1(o_ic, n_ic, scratch.as<G1Affine>());
+
+    // window sizes: full-width share guessed from the reference circuits
+    // (SURVEY §8 scalar make-up: ~1/3 of L, ~1/5 of A and B are full width)
+    uint32_t c_hl = env_u32("MB200_C_HL", choose_window(n_h + 0.33 * n_l));
+    uint32_t c_a = env_u32("MB200_C_A", choose_window(0.25 * n_a + 16));
+    uint32_t c_b1 = env_u32("MB200_C_B1", choose_window(0.25 * n_b1 + 16));
+    uint32_t c_b2 = env_u32("MB200_C_B2", choose_window(0.25 * n_b2 + 16));
+    P->k_hl = build_class<Fp>(P->t_hl, b_hl, P->sel_hl, n_h + n_l, c_hl, s);
+    P->k_a = build_class<Fp>(P->t_a, b_a, P->sel_a, n_a + 2, c_a, s);
+    P->k_b1 = build_class<Fp>(P->t_b1, b_b1, P->sel_b1, n_b1 + 1, c_b1, s);
+    P->k_b2 = build_class<Fp2>(P->t_b2, b_b2, P->sel_b2, n_b2 + 2, c_b2, s);
+    P->table_bytes = P->t_hl.bytes + P->t_a.bytes + P->t_b1.bytes + P->t_b2.bytes;
+    P->dom.build(P->log_m, s);
+
+    uint32_t bad_h = 0;
+    copy_d2h(&bad_h, bad.p, 4, s);
+    stream_sync(s);
+    if (bad_h) fail(MB200_EPARSE, "malformed point encoding in parameters%s", "");
+    return P.release();
+}
+
+// ---------------------------------------------------------------------------
+// prove
+// ---------------------------------------------------------------------------
+struct ProveCtx {  // one in-flight chunk: a stream and its scratch
+    cudaStream_t stream = 0;
+    DevBuf abc, w0, w1, w2, w3, pool, flag, res_hl, res_a, res_b1, res_b2, cmul, proofs;
+    MsmScratch msm;
+    bool have_stream = false;
+};
+
+struct ProveInputs {  // host or device pointers, selected by `on_device`
+    const uint8_t *a, *b, *c, *inputs, *aux, *r, *s;
+    bool on_device;
+};
+
+inline void copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                      bool src_on_device, cudaStream_t s) {
+#ifdef MB200_EMU
+    (void)src_on_device;
+    (void)s;
+    for (size_t i = 0; i < height; ++i) memcpy((char*)dst + i * dpitch, (const char*)src + i * spitch, width);
+#else
+    MB_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height,
+                              src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+#endif
+}
+
+// Enqueue one chunk of proofs [first, first + count) on ctx.stream.  proofs_out:
+// host memory, 192 bytes per proof.  No host synchronisation.
+inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, size_t first, uint32_t count,
+                        size_t rows, uint8_t* proofs_out) {
+    cudaStream_t s = x.stream;
+    const uint32_t m = P.m;
+    size_t polys = (size_t)count * 3;
+    x.abc.ensure(polys * rows * 32);
+    x.w0.ensure(polys * m * 32);
+    x.w1.ensure(polys * m * 32);
+    x.w2.ensure(polys * m * 32);
+    x.w3.ensure(polys * m * 32);
+    x.pool.ensure((size_t)count * P.pool_stride * 32);
+    x.res_hl.ensure(count * sizeof(G1XYZZ));
+    x.res_a.ensure(count * sizeof(G1XYZZ));
+    x.res_b1.ensure(count * sizeof(G1XYZZ));
+    x.res_b2.ensure(count * sizeof(G2XYZZ));
+    x.cmul.ensure((size_t)count * 2 * sizeof(G1XYZZ));
+    x.proofs.ensure((size_t)count * 192);
+
+    const size_t rb = rows * 32;
+    uint8_t* abc = x.abc.as<uint8_t>();
+    copy_rows(abc, 3 * rb, in.a + first * rb, rb, rb, count, in.on_device, s);
+    copy_rows(abc + rb, 3 * rb, in.b + first * rb, rb, rb, count, in.on_device, s);
+    copy_rows(abc + 2 * rb, 3 * rb, in.c + first * rb, rb, rb, count, in.on_device, s);
+    uint8_t* pool = x.pool.as<uint8_t>();
+    const size_t pitch = P.pool_stride * 32;
+    copy_rows(pool + P.idx_aux * 32, pitch, in.aux + first * P.n_aux * 32, (size_t)P.n_aux * 32, (size_t)P.n_aux * 32,
+              count, in.on_device, s);
+    copy_rows(pool + P.idx_inputs * 32, pitch, in.inputs + first * P.n_inputs * 32, (size_t)P.n_inputs * 32,
+              (size_t)P.n_inputs * 32, count, in.on_device, s);
+    copy_rows(pool + P.idx_r * 32, pitch, in.r + first * 32, 32, 32, count, in.on_device, s);
+    copy_rows(pool + P.idx_s * 32, pitch, in.s + first * 32, 32, 32, count, in.on_device, s);
+    FillOneArgs fo{count, x.pool.as<uint32_t>(), P.pool_stride, P.idx_one};
+    launch_pool_fill_one(fo, s);
+
+    h_pipeline(P.dom, count, (uint32_t)rows, x.abc.as<Fr>(), rows, x.pool.as<Fr>(), P.pool_stride, x.w0.as<Fr>(),
+               x.w1.as<Fr>(), x.w2.as<Fr>(), x.w3.as<Fr>(), s);
+
+    const uint32_t* pl = x.pool.as<uint32_t>();
+    msm_run<Fp>(P.k_hl, count, pl, P.pool_stride, x.res_hl.as<G1XYZZ>(), x.msm, s);
+    msm_run<Fp>(P.k_a, count, pl, P.pool_stride, x.res_a.as<G1XYZZ>(), x.msm, s);
+    msm_run<Fp>(P.k_b1, count, pl, P.pool_stride, x.res_b1.as<G1XYZZ>(), x.msm, s);
+    msm_run<Fp2>(P.k_b2, count, pl, P.pool_stride, x.res_b2.as<G2XYZZ>(), x.msm, s);
+
+    CmulArgs ca{(size_t)count * 2, x.res_a.as<G1XYZZ>(), x.res_b1.as<G1XYZZ>(), pl, P.pool_stride, P.idx_r, P.idx_s,
+                x.cmul.as<G1XYZZ>()};
+    launch_proof_cmul(ca, s);
+    FinishArgs fa{(size_t)count * 3, x.res_a.as<G1XYZZ>(), x.res_b2.as<G2XYZZ>(), x.res_hl.as<G1XYZZ>(),
+                  x.cmul.as<G1XYZZ>(), x.proofs.as<uint8_t>()};
+    launch_proof_finish(fa, s);
+    copy_d2h(proofs_out + first * 192, x.proofs.p, (size_t)count * 192, s);
+}
+
+}  // namespace mb

@@ -1,0 +1,397 @@
+"""Host-side mirror of the reference's proving surface over the C ABI.
+
+Mirrors, for the Groth16 path only:
+
+  * groth16::Parameters::read(reader, false)       masp_proofs/src/lib.rs:336-341
+  * load_parameters / parse_parameters             masp_proofs/src/lib.rs:278-403
+  * create_random_proof / create_proof             call sites masp_proofs/src/sapling/prover.rs:116-117, 201-202, 251-252
+  * LocalTxProver::{new, from_bytes, with_default_location, spend_proof,
+    output_proof, convert_proof}                   masp_proofs/src/prover.rs:55-136, 156-261
+
+Witness synthesis (Circuit::synthesize into bellman's ProvingAssignment) is
+above this path (NEXT-1): the *_proof methods take the
+ProvingAssignment a Rust caller would hand to the FFI -- the per-row
+evaluations a, b, c, the input and aux assignments -- plus, at key load, the
+three density bitmaps.  jubjub-side bookkeeping of SaplingProvingContext
+(bsk, cv_sum, binding_sig) is not Groth16 work and stays with the caller.
+"""
+import ctypes
+import hashlib
+import os
+from dataclasses import dataclass
+
+from . import _lib
+from ._lib import Mb200Error, check
+
+GROTH_PROOF_SIZE = 192  # masp_primitives/src/transaction/components.rs:14-15
+
+# masp_proofs/src/lib.rs:61-76
+MASP_SPEND_NAME = "masp-spend.params"
+MASP_OUTPUT_NAME = "masp-output.params"
+MASP_CONVERT_NAME = "masp-convert.params"
+MASP_SPEND_HASH = "196e7c717f25e16653431559ce2c8816e750a4490f98696e3c031efca37e25e0647182b7b013660806db11eb2b1e365fb2d6a0f24dbbd9a4a8314fef10a7cba2"
+MASP_OUTPUT_HASH = "eafc3b1746cccc8b9eed2b69395692c5892f6aca83552a07dceb2dcbaa64dcd0e22434260b3aa3b049b633a08b008988cbe0d31effc77e2bc09bfab690a23724"
+MASP_CONVERT_HASH = "dc4aaf3c3ce056ab448b6c4a7f43c1d68502c2902ea89ab8769b1524a2e8ace9a5369621a73ee1daa52aec826907a19974a37874391cf8f11bbe0b0420de1ab7"
+MASP_SPEND_BYTES = 49848572
+MASP_CONVERT_BYTES = 22570940
+MASP_OUTPUT_BYTES = 16398620
+
+R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+_initialised = False
+
+
+def init(device=None):
+    """Bind this process to one GPU (default: the current CUDA device)."""
+    global _initialised
+    L = _lib.lib()
+    if device is None:
+        check(L.mb200_init(None, 0))
+    else:
+        ids = (ctypes.c_int * 1)(int(device))
+        check(L.mb200_init(ids, 1))
+    _initialised = True
+
+
+def _ensure_init():
+    if not _initialised:
+        init()
+
+
+def set_option(name, value):
+    _ensure_init()
+    check(_lib.lib().mb200_set_option(name.encode(), int(value)))
+
+
+def get_counter(name):
+    v = ctypes.c_double()
+    check(_lib.lib().mb200_get_counter(name.encode(), ctypes.byref(v)))
+    return v.value
+
+
+def _ptr(x):
+    """Host bytes-like or an integer device / pinned-host address -> c_void_p."""
+    if isinstance(x, int):
+        return ctypes.c_void_p(x)
+    if isinstance(x, (bytes, bytearray)):
+        return ctypes.cast(ctypes.c_char_p(bytes(x)) if isinstance(x, bytearray) else ctypes.c_char_p(x), ctypes.c_void_p)
+    if hasattr(x, "ctypes"):  # numpy array
+        return ctypes.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):  # torch tensor
+        return ctypes.c_void_p(x.data_ptr())
+    raise TypeError("unsupported buffer type %r" % type(x))
+
+
+class Parameters:
+    """groth16::Parameters<Bls12>, device resident.
+
+    `densities` = (a_aux_density, b_input_density, b_aux_density) bitmaps
+    (LSB-first) as bellman's ProvingAssignment records them for the circuit;
+    None means every variable is dense in that query."""
+
+    def __init__(self, handle, info):
+        self._h = handle
+        (self.n_inputs, self.n_aux, self.h_len, self.a_len, self.b_len, self.m, self.consumed,
+         self.table_bytes, self.window_hl, self.window_a) = info
+
+    @classmethod
+    def read(cls, buf, densities=None, checked=False):
+        """Parameters::read(reader, checked); the reference passes checked = false
+        (masp_proofs/src/lib.rs:336-341) and so does this path: encodings must be
+        well formed, curve / subgroup membership is not tested."""
+        if checked:
+            raise NotImplementedError("checked = true is not on the reference's path (lib.rs:336-341)")
+        _ensure_init()
+        a_d, bi_d, ba_d = densities if densities is not None else (None, None, None)
+        h = ctypes.c_void_p()
+        buf = bytes(buf) if not isinstance(buf, bytes) else buf
+        check(_lib.lib().mb200_params_load(buf, len(buf), a_d, bi_d, ba_d, ctypes.byref(h)))
+        info = (ctypes.c_uint64 * 10)()
+        check(_lib.lib().mb200_params_info(h, info))
+        return cls(h, [int(x) for x in info])
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().mb200_params_free(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+@dataclass
+class ProvingAssignment:
+    """What bellman's ProvingAssignment holds after Circuit::synthesize plus
+    the prover's extra `input_i * 0 = 0` rows: rows = n_constraints + n_inputs.
+    All fields are concatenated 32-byte little-endian canonical scalars."""
+    a: bytes
+    b: bytes
+    c: bytes
+    input_assignment: bytes
+    aux_assignment: bytes
+
+    @property
+    def rows(self):
+        return len(self.a) // 32
+
+
+def create_proof_batch(assignments, params, r_s, s_s):
+    """bellperson create_proof_batch(circuits, params, r_s, s_s) after synthesis.
+    Returns a list of 192-byte proofs (Proof::write)."""
+    n = len(assignments)
+    if n == 0:
+        return []
+    if len(r_s) != n or len(s_s) != n:
+        raise ValueError("r_s / s_s length mismatch")
+    rows = assignments[0].rows
+    for x in assignments:
+        if (x.rows != rows or len(x.b) != len(x.a) or len(x.c) != len(x.a)
+                or len(x.input_assignment) != 32 * params.n_inputs or len(x.aux_assignment) != 32 * params.n_aux):
+            raise ValueError("assignment shape does not match the parameters")
+    cat = lambda f: b"".join(f(x) for x in assignments)
+    to32 = lambda v: v if isinstance(v, (bytes, bytearray)) else int(v).to_bytes(32, "little")
+    out = prove_batch_raw(params, n, rows, cat(lambda x: x.a), cat(lambda x: x.b), cat(lambda x: x.c),
+                          cat(lambda x: x.input_assignment), cat(lambda x: x.aux_assignment),
+                          b"".join(to32(v) for v in r_s), b"".join(to32(v) for v in s_s))
+    return [out[192 * i:192 * (i + 1)] for i in range(n)]
+
+
+def prove_batch_raw(params, n_proofs, rows, a, b, c, inputs, aux, r, s, device=False, out=None):
+    """Thin call of mb200_prove_batch / mb200_prove_batch_device.  Buffers are
+    bytes, numpy arrays, torch tensors or raw addresses; with device=True they
+    are device pointers.  Returns n_proofs * 192 bytes."""
+    _ensure_init()
+    L = _lib.lib()
+    buf = out if out is not None else ctypes.create_string_buffer(192 * n_proofs)
+    outp = _ptr(out) if out is not None else ctypes.cast(buf, ctypes.c_void_p)
+    fn = L.mb200_prove_batch_device if device else L.mb200_prove_batch
+    keep = [a, b, c, inputs, aux, r, s]
+    check(fn(params._h, n_proofs, rows, *[_ptr(x) for x in keep], outp))
+    return buf.raw if out is None else out
+
+
+def create_proof(assignment, params, r, s):
+    """bellman create_proof(circuit, params, r, s) after synthesis -> 192 bytes."""
+    return create_proof_batch([assignment], params, [r], [s])[0]
+
+
+def _os_rng_scalar():
+    # OsRng + Fr::random: uniform below r by rejection on 255-bit draws
+    while True:
+        v = int.from_bytes(os.urandom(32), "little") & ((1 << 255) - 1)
+        if v < R_ORDER:
+            return v
+
+
+def create_random_proof(assignment, params, rng=_os_rng_scalar):
+    """create_random_proof(circuit, params, &mut OsRng): r, s drawn here, as the
+    reference does inside spend_proof / output_proof / convert_proof
+    (masp_proofs/src/sapling/prover.rs:66, 174, 225)."""
+    return create_proof(assignment, params, rng(), rng())
+
+
+# ---------------------------------------------------------------------------
+# load_parameters / LocalTxProver
+# ---------------------------------------------------------------------------
+class ParameterError(Exception):
+    """The reference panics here (masp_proofs/src/lib.rs:290-293, 316-318, 359-388)."""
+
+
+def _verify_file_size(path, expected, name):
+    size = os.path.getsize(path)
+    if size != expected:
+        raise ParameterError("%s parameter file size is not correct: %d, expected %d" % (name, size, expected))
+
+
+def parse_parameters(spend_bytes, output_bytes, convert_bytes, densities=None, verify_hashes=True):
+    """parse_parameters (masp_proofs/src/lib.rs:330-403): Parameters::read on each
+    stream, then the whole stream -- including the MPC transcript after the
+    key -- is BLAKE2b-512 hashed and compared with the pinned constants."""
+    dens = densities or {}
+    out = {}
+    for name, buf, want in (("spend", spend_bytes, MASP_SPEND_HASH), ("output", output_bytes, MASP_OUTPUT_HASH),
+                            ("convert", convert_bytes, MASP_CONVERT_HASH)):
+        if verify_hashes:
+            got = hashlib.blake2b(buf, digest_size=64).hexdigest()
+            if got != want:
+                raise ParameterError("MASP %s parameter file is not correct (BLAKE2b %s...)" % (name, got[:16]))
+        out[name] = Parameters.read(buf, dens.get(name))
+    return out
+
+
+def load_parameters(spend_path, output_path, convert_path, densities=None, verify=True):
+    """load_parameters (masp_proofs/src/lib.rs:278-325)."""
+    if verify:
+        _verify_file_size(spend_path, MASP_SPEND_BYTES, "masp spend")
+        _verify_file_size(output_path, MASP_OUTPUT_BYTES, "masp output")
+        _verify_file_size(convert_path, MASP_CONVERT_BYTES, "masp convert")
+    rd = lambda p: open(p, "rb").read()
+    return parse_parameters(rd(spend_path), rd(output_path), rd(convert_path), densities, verify_hashes=verify)
+
+
+def default_params_folder():
+    """masp_proofs/src/lib.rs:100-108."""
+    return os.path.join(os.path.expanduser("~"), ".masp-params")
+
+
+class LocalTxProver:
+    """masp_proofs::prover::LocalTxProver restricted to its Groth16 work."""
+
+    def __init__(self, spend_params, output_params, convert_params):
+        self.spend_params = spend_params
+        self.output_params = output_params
+        self.convert_params = convert_params
+
+    @classmethod
+    def new(cls, spend_path, output_path, convert_path, densities=None, verify=True):
+        p = load_parameters(spend_path, output_path, convert_path, densities, verify)
+        return cls(p["spend"], p["output"], p["convert"])
+
+    @classmethod
+    def from_bytes(cls, spend_param_bytes, output_param_bytes, convert_param_bytes, densities=None,
+                   verify_hashes=True):
+        p = parse_parameters(spend_param_bytes, output_param_bytes, convert_param_bytes, densities, verify_hashes)
+        return cls(p["spend"], p["output"], p["convert"])
+
+    @classmethod
+    def with_default_location(cls, densities=None):
+        d = default_params_folder()
+        paths = [os.path.join(d, n) for n in (MASP_SPEND_NAME, MASP_OUTPUT_NAME, MASP_CONVERT_NAME)]
+        if not all(os.path.exists(p) for p in paths):
+            return None  # the reference returns None (prover.rs:120-136)
+        return cls.new(*paths, densities=densities)
+
+    # Each returns the [u8; 192] zkproof of the description.
+    def spend_proof(self, assignment, rng=_os_rng_scalar):
+        return create_random_proof(assignment, self.spend_params, rng)
+
+    def output_proof(self, assignment, rng=_os_rng_scalar):
+        return create_random_proof(assignment, self.output_params, rng)
+
+    def convert_proof(self, assignment, rng=_os_rng_scalar):
+        return create_random_proof(assignment, self.convert_params, rng)
+
+    def prove_bundle(self, spends=(), converts=(), outputs=(), rng=_os_rng_scalar):
+        """All descriptions of a transaction in one launch per circuit (the
+        batching TxProver of SURVEY.md §8f-2): returns three lists of proofs."""
+        res = []
+        for params, group in ((self.spend_params, spends), (self.convert_params, converts),
+                              (self.output_params, outputs)):
+            group = list(group)
+            res.append(create_proof_batch(group, params, [rng() for _ in group], [rng() for _ in group]))
+        return tuple(res)
+
+
+# ---------------------------------------------------------------------------
+# standalone pieces of the path
+# ---------------------------------------------------------------------------
+def msm_g1(bases, scalars, n):
+    _ensure_init()
+    out = ctypes.create_string_buffer(96)
+    check(_lib.lib().mb200_msm_g1(_ptr(bases), _ptr(scalars), n, ctypes.cast(out, ctypes.c_void_p)))
+    return out.raw
+
+
+def msm_g2(bases, scalars, n):
+    _ensure_init()
+    out = ctypes.create_string_buffer(192)
+    check(_lib.lib().mb200_msm_g2(_ptr(bases), _ptr(scalars), n, ctypes.cast(out, ctypes.c_void_p)))
+    return out.raw
+
+
+class G1Bases:
+    """Device-resident decoded bases for repeated / split MSMs."""
+
+    def __init__(self, bases, n):
+        _ensure_init()
+        self.n = n
+        self._p = ctypes.c_void_p()
+        check(_lib.lib().mb200_g1_bases_upload(_ptr(bases), n, ctypes.byref(self._p)))
+
+    def msm_partial(self, scalars, n=None):
+        out = ctypes.create_string_buffer(192)
+        check(_lib.lib().mb200_msm_g1_partial(self._p, _ptr(scalars), self.n if n is None else n,
+                                              ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw
+
+    def __del__(self):
+        p = getattr(self, "_p", None)
+        if p:
+            try:
+                _lib.lib().mb200_dev_free(p)
+            except Exception:
+                pass
+            self._p = None
+
+
+def g1_sum_partials(partials):
+    _ensure_init()
+    buf = b"".join(partials)
+    out = ctypes.create_string_buffer(96)
+    check(_lib.lib().mb200_g1_sum_partials(_ptr(buf), len(partials), ctypes.cast(out, ctypes.c_void_p)))
+    return out.raw
+
+
+def ntt(data, log_n, inverse=False, coset=False):
+    _ensure_init()
+    buf = ctypes.create_string_buffer(bytes(data), len(data))
+    check(_lib.lib().mb200_ntt(ctypes.cast(buf, ctypes.c_void_p), log_n, int(inverse), int(coset)))
+    return buf.raw
+
+
+def h_coeffs(a, b, c, rows):
+    _ensure_init()
+    m = 1
+    while m < rows:
+        m *= 2
+    out = ctypes.create_string_buffer(32 * (m - 1))
+    check(_lib.lib().mb200_h_coeffs(_ptr(a), _ptr(b), _ptr(c), rows, ctypes.cast(out, ctypes.c_void_p)))
+    return out.raw
+
+
+def fr_mul(a, b, n):
+    _ensure_init()
+    out = ctypes.create_string_buffer(32 * n)
+    check(_lib.lib().mb200_fr_mul(_ptr(a), _ptr(b), n, ctypes.cast(out, ctypes.c_void_p)))
+    return out.raw
+
+
+def fr_mul_device(a_ptr, b_ptr, n, out_ptr):
+    _ensure_init()
+    check(_lib.lib().mb200_fr_mul_device(_ptr(a_ptr), _ptr(b_ptr), n, _ptr(out_ptr)))
+
+
+def params_synthesize(shape, seed=None):
+    """generate_random_parameters stand-in: Parameters bytes of `shape`
+    (masp_b200.synthetic.Shape) with known discrete logs."""
+    from .synthetic import MASTER_SEED
+    _ensure_init()
+    seed = MASTER_SEED if seed is None else seed
+    L = _lib.lib()
+    n = L.mb200_params_synth_size(shape.n_inputs, shape.h_len, shape.n_aux, shape.a_len, shape.b_len)
+    out = ctypes.create_string_buffer(n)
+    check(L.mb200_params_synthesize(seed, shape.n_inputs, shape.h_len, shape.n_aux, shape.a_len, shape.b_len,
+                                    ctypes.cast(out, ctypes.c_void_p), n))
+    return out.raw
+
+
+def synth_points(stream, start, n, group=1, seed=None):
+    from .synthetic import MASTER_SEED
+    _ensure_init()
+    seed = MASTER_SEED if seed is None else seed
+    out = ctypes.create_string_buffer(n * (96 if group == 1 else 192))
+    check(_lib.lib().mb200_synth_points(seed, stream, start, n, group, ctypes.cast(out, ctypes.c_void_p)))
+    return out.raw
+
+
+def selftest():
+    _ensure_init()
+    return _lib.lib().mb200_selftest()
+
+
+def bench_fpmul():
+    _ensure_init()
+    v = ctypes.c_double()
+    check(_lib.lib().mb200_bench_fpmul(ctypes.byref(v)))
+    return v.value

@@ -1,0 +1,61 @@
+"""The device code compiled for the host (tests/emu/libmasp_b200_emu.so) against
+the oracle: launch orchestration, bucket indexing, scan / scatter, reduction
+levels, Stockham passes and chunking, all on CPU.  A test aid only: the product
+library has no CPU path (tests/test_abi.py)."""
+import pytest
+
+from masp_b200 import synthetic as syn
+from util import ib, rand_scalars, assignment, oracle_proofs
+
+
+def test_selftest(emu):
+    assert emu.selftest() == 0
+
+
+def test_ntt_and_h(emu, oracle):
+    for log_n in (1, 2, 3, 4, 5, 7, 10):
+        v = ib(rand_scalars(1 << log_n, log_n, "uniform"))
+        for inv in (False, True):
+            for cos in (False, True):
+                assert emu.ntt(v, log_n, inv, cos) == oracle.ntt(v, log_n, inv, cos), (log_n, inv, cos)
+    for rows in (2, 9, 100, 300):
+        a, b = ib(rand_scalars(rows, 1, "uniform")), ib(rand_scalars(rows, 2, "uniform"))
+        c = oracle.fr_mul(a, b, rows)
+        assert emu.fr_mul(a, b, rows) == c
+        assert emu.h_coeffs(a, b, c, rows) == oracle.h_coeffs(a, b, c, rows)
+
+
+def test_msm(emu, oracle):
+    logs = syn.fr_uniform(syn.MASTER_SEED, 12, 300)
+    bases = oracle.g1_gen_mul(syn.limbs_to_bytes(logs), 300)
+    assert emu.synth_points(12, 0, 20, 1) == bases[:96 * 20]
+    for n in (0, 1, 5, 40, 300):
+        sc = ib(rand_scalars(n, n))
+        assert emu.msm_g1(bases[:96 * n], sc, n) == oracle.msm_g1(bases[:96 * n], sc, n), n
+    b2 = oracle.g2_gen_mul(syn.limbs_to_bytes(logs[:12]), 12)
+    sc = ib(rand_scalars(12, 77))
+    assert emu.msm_g2(b2, sc, 12) == oracle.msm_g2(b2, sc, 12)
+    parts = [emu.G1Bases(bases[96 * lo:96 * hi], hi - lo).msm_partial(ib(rand_scalars(300, 5))[32 * lo:32 * hi])
+             for lo, hi in ((0, 100), (100, 300))]
+    assert emu.g1_sum_partials(parts) == oracle.msm_g1(bases, ib(rand_scalars(300, 5)), 300)
+
+
+@pytest.mark.slow
+def test_prove_batch_chunked(emu, oracle):
+    sh = syn.tiny_shape()
+    kb = emu.params_synthesize(sh)
+    assert kb == oracle.params_from_logs(syn.key_logs(sh))
+    dens = sh.densities()
+    P = emu.Parameters.read(kb, dens)
+    assert (P.n_inputs, P.n_aux, P.h_len, P.a_len, P.b_len, P.m) == (sh.n_inputs, sh.n_aux, sh.h_len, sh.a_len,
+                                                                     sh.b_len, sh.m)
+    ws = [syn.witness(sh, i, oracle.fr_mul) for i in range(5)]
+    emu.set_option("chunk", 2)
+    got = emu.create_proof_batch([assignment(emu, w) for w in ws], P, [w["r"] for w in ws], [w["s"] for w in ws])
+    assert got == oracle_proofs(oracle, kb, sh, dens, ws)
+    bad = bytearray(ws[0]["aux"])
+    bad[0:32] = syn.R_INT.to_bytes(32, "little")
+    w = dict(ws[0], aux=bytes(bad))
+    with pytest.raises(emu.Mb200Error) as e:
+        emu.create_proof(assignment(emu, w), P, w["r"], w["s"])
+    assert e.value.code == -6
