@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Headline benchmark: Groth16 proofs/s for the MASP Spend circuit shape
+(BASELINE.json configs[1]: Spend, ~2^17 constraints, batch = 256 proofs per
+GPU, synthetic witnesses, explicit r/s), one process per GPU.
+
+  python bench.py --gpus 1 --steps K --warmup W            # this framework
+  python bench.py --impl reference --gpus 1 --steps K ...  # restated bellperson CPU prover on the host cores
+
+A step is one pass of the hot path over one batch: for every proof the 7-NTT
+H pipeline, the four bucket MSMs (H+L, A, B1 over G1; B2 over G2), assembly
+and 192-byte encoding.  `value` is measured with the batch already resident
+in HBM; `e2e` goes through mb200_prove_batch with pinned HOST buffers
+(host->device copies of every witness and the device->host read of the
+proofs inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from masp_b200 import synthetic as syn  # noqa: E402
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]),
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples),
+                "reasons": sorted(reasons)}
+
+
+def make_batch(shape, batch, first_index, torch, pv):
+    """Synthetic witnesses for proofs [first_index, first_index + batch) in
+    pinned host memory (SURVEY §8d distribution); c = a * b by the device
+    kernel behind mb200_fr_mul_device."""
+    rows, n_aux, n_in = shape.rows, shape.n_aux, shape.n_inputs
+    pin = lambda n: torch.empty(n, dtype=torch.uint8).pin_memory()
+    host = {"a": pin(batch * rows * 32), "b": pin(batch * rows * 32), "c": pin(batch * rows * 32),
+            "aux": pin(batch * n_aux * 32), "inputs": pin(batch * n_in * 32), "r": pin(batch * 32), "s": pin(batch * 32)}
+    view = {k: v.numpy().view("<u8") for k, v in host.items()}
+    cls = shape.aux_classes()
+    is_bool = (cls & 4) != 0
+    for i in range(batch):
+        base = syn.STREAM_WIT_A + 8 * (first_index + i)
+        a = syn.fr_uniform(syn.MASTER_SEED, base + 0, rows)
+        b = syn.fr_uniform(syn.MASTER_SEED, base + 1, rows)
+        inputs = syn.fr_uniform(syn.MASTER_SEED, base + 2, n_in)
+        inputs[0] = (1, 0, 0, 0)
+        a[shape.n_constraints:] = inputs
+        b[shape.n_constraints:] = 0
+        aux = syn.fr_uniform(syn.MASTER_SEED, base + 3, n_aux)
+        bits = syn.fr_bits(syn.MASTER_SEED, base + 4, n_aux)
+        aux[is_bool] = bits[is_bool]
+        rs = syn.fr_uniform(syn.MASTER_SEED, base + 5, 2)
+        view["a"][i * rows * 4:(i + 1) * rows * 4] = a.reshape(-1)
+        view["b"][i * rows * 4:(i + 1) * rows * 4] = b.reshape(-1)
+        view["aux"][i * n_aux * 4:(i + 1) * n_aux * 4] = aux.reshape(-1)
+        view["inputs"][i * n_in * 4:(i + 1) * n_in * 4] = inputs.reshape(-1)
+        view["r"][i * 4:(i + 1) * 4] = rs[0]
+        view["s"][i * 4:(i + 1) * 4] = rs[1]
+    dev = {k: v.cuda(non_blocking=True) for k, v in host.items()}
+    torch.cuda.synchronize()
+    pv.fr_mul_device(dev["a"], dev["b"], batch * rows, dev["c"])
+    host["c"].copy_(dev["c"])
+    torch.cuda.synchronize()
+    return host, dev
+
+
+def cpu_reference_setup(shape, key_bytes):
+    from oracle import c_oracle as co
+    return co, co.Params(key_bytes, shape.n_aux, *shape.densities())
+
+
+def cpu_prove(co_params, shape, host, i):
+    rows, n_aux, n_in = shape.rows, shape.n_aux, shape.n_inputs
+    g = lambda k, per: bytes(host[k].numpy()[i * per * 32:(i + 1) * per * 32])
+    return co_params.prove(rows, g("a", rows), g("b", rows), g("c", rows), g("inputs", n_in), g("aux", n_aux),
+                           g("r", 1), g("s", 1), timings=True)
+
+
+def run_reference(args, shape):
+    """The reference's own CPU implementation of the path, restated
+    (oracle/c: window-parallel Pippenger + radix-2 domain on all host cores;
+    the Rust crates are not vendored and there is no cargo here)."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from oracle import c_oracle as co
+    sample = args.ref_sample
+    key = co.params_from_logs(syn.key_logs(shape))
+    P = co.Params(key, shape.n_aux, *shape.densities())
+    ws = [syn.witness(shape, i, co.fr_mul) for i in range(sample)]
+    prove = lambda w: P.prove(shape.rows, w["a"], w["b"], w["c"], w["inputs"], w["aux"], w["r"], w["s"])
+    for _ in range(args.warmup):
+        prove(ws[0])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for w in ws:
+            prove(w)
+    dt = time.perf_counter() - t0
+    value = args.steps * sample / dt
+    cores = co.get_threads()
+    line = {
+        "impl": "reference", "metric": "spend_proofs_per_sec", "value": value, "unit": "proofs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (mod p 381-bit / mod r 255-bit)",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: Spend shape (rows 100645, m 2^17), explicit r/s; bounded sample of %d proofs per step" % sample,
+                   "circuit": shape.name, "batch_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": cores, "kind": "port",
+                         "sample": "%d Spend-shaped proofs per step x %d steps, restated bellperson CPU prover (oracle/c)" % (sample, args.steps)},
+        "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--circuit", default="spend", choices=list(syn.SHAPES))
+    ap.add_argument("--batch", type=int, default=256, help="proofs per GPU per step")
+    ap.add_argument("--chunk", type=int, default=0, help="proofs per in-flight chunk (0 = library default)")
+    ap.add_argument("--streams", type=int, default=0)
+    ap.add_argument("--ref-sample", type=int, default=2, help="--impl reference: proofs per step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget on rank 0")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    shape = syn.SHAPES[args.circuit]
+
+    if args.impl == "reference":
+        run_reference(args, shape)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import masp_b200.prover as pv
+    pv.init(local)
+    if args.chunk:
+        pv.set_option("chunk", args.chunk)
+    if args.streams:
+        pv.set_option("streams", args.streams)
+
+    t_setup = time.perf_counter()
+    key = pv.params_synthesize(shape)
+    params = pv.Parameters.read(key, shape.densities())
+    t_key = time.perf_counter() - t_setup
+    B = args.batch
+    host, dev = make_batch(shape, B, rank * B, torch, pv)
+    t_setup = time.perf_counter() - t_setup
+    rows = shape.rows
+    out_pinned = torch.empty(B * 192, dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        pv.prove_batch_raw(params, B, rows, dev["a"], dev["b"], dev["c"], dev["inputs"], dev["aux"], dev["r"],
+                           dev["s"], device=True, out=out_pinned)
+        return pv.get_counter("last_batch_us") * 1e-3
+
+    def step_host():
+        pv.prove_batch_raw(params, B, rows, host["a"], host["b"], host["c"], host["inputs"], host["aux"], host["r"],
+                           host["s"], device=False, out=out_pinned)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = pv.get_counter("launches")
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        dev_ms += step_device()
+    barrier()
+    wall = time.perf_counter() - t0
+    launches = pv.get_counter("launches") - launches0
+    wall = max_over_ranks(wall)
+    dev_ms = max_over_ranks(dev_ms)
+    proofs_dev = bytes(out_pinned.numpy())
+
+    # end to end: pinned host buffers in, proofs out, copies inside the timed region
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    wall_e2e = max_over_ranks(time.perf_counter() - t0)
+    if rank == 0:
+        sampler.stop_flag = True
+    assert bytes(out_pinned.numpy()) == proofs_dev, "host-buffer and device-buffer paths disagree"
+
+    # roofline of the dominant kernel (G1/G2 bucket accumulation), timed live with CUDA events per launch
+    pv.set_option("profile", 1)
+    step_device()
+    acc_us, acc_n, acc_bytes = pv.get_counter("acc_us"), pv.get_counter("acc_launches"), pv.get_counter("acc_bytes")
+    step_ms_profiled = pv.get_counter("last_batch_us") * 1e-3
+    pv.set_option("profile", 0)
+    fpmul = pv.bench_fpmul()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    achieved = acc_bytes / (acc_us * 1e-6) / 1e9 if acc_us else 0.0
+    ms_per_step = 1e3 * wall / args.steps
+    value = world * B * args.steps / wall
+    e2e_value = world * B * args.steps / wall_e2e
+    h2d = B * 32 * (3 * rows + shape.n_aux + shape.n_inputs + 2)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("msm_accumulate_g1_dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    line = {
+        "metric": "spend_proofs_per_sec" if shape.name == "spend" else shape.name + "_proofs_per_sec",
+        "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "device_ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (mod p 381-bit / mod r 255-bit)",
+        "data": "synthetic",
+        "config": {
+            "workload": "configs[1]: %s shape (constraints %d, rows %d, m 2^%d), batch %d proofs per GPU, explicit r/s, "
+                        "synthetic witnesses (%.1f%% boolean aux)" % (shape.name, shape.n_constraints, rows, shape.log_m, B,
+                                                                    100.0 * shape.n_bool / shape.n_aux),
+            "circuit": shape.name, "batch_per_gpu": B, "parallelism": "proof-sharded x%d, no collective" % world,
+            "l2": "inputs per step (%.2f GB) are larger than the 126 MB L2" % (h2d / 1e9),
+            "window_bits": {"h_l": params.window_hl, "a": params.window_a},
+            "table_bytes_hbm": params.table_bytes, "algorithmic_bytes_per_proof": shape.algorithmic_bytes(),
+            "setup_s": round(t_setup, 2), "key_synth_and_load_s": round(t_key, 2),
+        },
+        "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 192,
+                "ms_per_step": 1e3 * wall_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": {
+            "bound": "hbm", "kernel": "msm_accumulate_g1/g2 (bucket accumulation, all four queries)",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "peak_source": peak_src, "launches_timed": int(acc_n),
+            "algorithmic_bytes_per_launch": acc_bytes / acc_n if acc_n else 0,
+            "avg_launch_ms": acc_us * 1e-3 / acc_n if acc_n else 0,
+            "share_of_step": (acc_us * 1e-3) / step_ms_profiled if step_ms_profiled else None,
+            "note": "this path is bound by 32-bit integer multiply-add issue, not HBM (SURVEY.md §7/§8d): "
+                    "see fp_mul_per_s for the integer-side figure",
+            "fp_mul_per_s": fpmul,
+            "whole_proof_hbm_frac": shape.algorithmic_bytes() * value / world / 1e9 / peak,
+        },
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        co, P = cpu_reference_setup(shape, key)
+        t0 = time.perf_counter()
+        done, parity = 0, 0
+        breakdown = np.zeros(8)
+        while done < min(B, 16) and (done < 2 or time.perf_counter() - t0 < args.cpu_seconds):
+            proof, tm = cpu_prove(P, shape, host, done)
+            breakdown += np.array(tm)
+            if proof == proofs_dev[192 * done:192 * (done + 1)]:
+                parity += 1
+            done += 1
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": done / dt, "unit": "proofs/s", "cores": co.get_threads(), "kind": "port",
+            "sample": "first %d proofs of the same batch (%.1f s), restated bellperson CPU prover (oracle/c), "
+                      "all host threads" % (done, dt),
+            "seconds_per_proof": dt / done,
+            "breakdown_s_per_proof": {"h_ntt_wall": breakdown[0] / done, "msm_wall": breakdown[1] / done,
+                                      "assembly_wall": breakdown[2] / done},
+            "gpu_proofs_byte_identical": "%d/%d" % (parity, done),
+        }
+        if parity != done:
+            line["parity_error"] = "GPU proofs differ from the CPU oracle"
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -36,26 +36,5 @@ def emu():
     orchestration and index arithmetic on CPU.  Never a product path; it is
     bound to a private copy of the ctypes layer so the package's own library
     handle is untouched."""
-    import importlib.util
-    from masp_b200 import _lib
-    from masp_b200.build import build_emu
-    handle = _lib.bind(build_emu())
-    spec = importlib.util.find_spec("masp_b200.prover")
-    mod = importlib.util.module_from_spec(spec)
-
-    class _EmuLib:
-        Mb200Error = _lib.Mb200Error
-
-        @staticmethod
-        def lib():
-            return handle
-
-        @staticmethod
-        def check(rc):
-            if rc != 0:
-                raise _lib.Mb200Error(rc, handle.mb200_last_error().decode(errors="replace"))
-    spec.loader.exec_module(mod)
-    mod._lib = _EmuLib
-    mod.check = _EmuLib.check
-    mod.init()
-    return mod
+    from util import load_emu
+    return load_emu()

@@ -22,3 +22,30 @@ def assignment(pv, w):
 def oracle_proofs(co, key_bytes, shape, dens, ws):
     P = co.Params(key_bytes, shape.n_aux, *dens)
     return [P.prove(shape.rows, w["a"], w["b"], w["c"], w["inputs"], w["aux"], w["r"], w["s"]) for w in ws]
+
+
+def load_emu():
+    """masp_b200.prover bound to the host-compiled device code (tests/emu)."""
+    import importlib.util
+    from masp_b200 import _lib
+    from masp_b200.build import build_emu
+    handle = _lib.bind(build_emu())
+    spec = importlib.util.find_spec("masp_b200.prover")
+    mod = importlib.util.module_from_spec(spec)
+
+    class _EmuLib:
+        Mb200Error = _lib.Mb200Error
+
+        @staticmethod
+        def lib():
+            return handle
+
+        @staticmethod
+        def check(rc):
+            if rc != 0:
+                raise _lib.Mb200Error(rc, handle.mb200_last_error().decode(errors="replace"))
+    spec.loader.exec_module(mod)
+    mod._lib = _EmuLib
+    mod.check = _EmuLib.check
+    mod.init()
+    return mod
