@@ -26,7 +26,7 @@ struct State {
     int device = 0;
     cudaStream_t main = 0;
     std::vector<ProveCtx> ctxs;
-    uint32_t chunk = 16;
+    uint32_t chunk = 64;
     std::map<unsigned, NttCache*> ntt;
     MsmScratch msm;
     std::mutex mu;
@@ -40,13 +40,27 @@ static void require_init() {
 static void set_ctx_count(size_t n) {
 #ifndef MB200_EMU
     for (auto& c : g.ctxs)
-        if (c.have_stream) cudaStreamDestroy(c.stream);
+        if (c.have_stream) {
+            cudaStreamSynchronize(c.stream);
+            cudaStreamDestroy(c.stream);
+            cudaEventDestroy(c.ev_inputs);
+            for (int i = 0; i < 3; ++i) {
+                cudaStreamSynchronize(c.side[i]);
+                cudaStreamDestroy(c.side[i]);
+                cudaEventDestroy(c.ev_side[i]);
+            }
+        }
 #endif
     g.ctxs.clear();
     g.ctxs.resize(n);
 #ifndef MB200_EMU
     for (auto& c : g.ctxs) {
         MB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        MB_CUDA(cudaEventCreateWithFlags(&c.ev_inputs, cudaEventDisableTiming));
+        for (int i = 0; i < 3; ++i) {
+            MB_CUDA(cudaStreamCreateWithFlags(&c.side[i], cudaStreamNonBlocking));
+            MB_CUDA(cudaEventCreateWithFlags(&c.ev_side[i], cudaEventDisableTiming));
+        }
         c.have_stream = true;
     }
 #endif
@@ -225,8 +239,8 @@ int mb200_init(const int* device_ids, int n_devices) {
     (void)device_ids;
     (void)n_devices;
 #endif
-    g.chunk = env_u32("MB200_CHUNK", 16);
-    set_ctx_count(env_u32("MB200_STREAMS", 2));
+    g.chunk = env_u32("MB200_CHUNK", 64);
+    set_ctx_count(env_u32("MB200_STREAMS", 3));
     g.inited = true;
     MB_API_END
 }

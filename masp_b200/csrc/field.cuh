@@ -233,8 +233,15 @@ struct Mont {
         od[N - 1] = addc(od[N - 1], 0);
     }
 
-    // r = a * b * 2^(-32N) mod p
-    MB_HD static Mont mul(const Mont& a, const Mont& b) {
+    // r = a * b * 2^(-32N) mod p.  Units that hold only latency-bound code
+    // (MB_COLD_MUL) call one out-of-line body: their kernels are a few hundred
+    // instructions instead of tens of thousands and stay in the instruction cache.
+#ifdef MB_COLD_MUL
+    MB_COLD Mont mul(const Mont& a, const Mont& b) { return mul_inline(a, b); }
+#else
+    MB_HD static Mont mul(const Mont& a, const Mont& b) { return mul_inline(a, b); }
+#endif
+    MB_HD static Mont mul_inline(const Mont& a, const Mont& b) {
         uint32_t ev[N], od[N];
         // first row: plain products
         MB_UNROLL

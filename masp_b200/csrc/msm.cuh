@@ -165,7 +165,7 @@ MB_HD void scan_write_body(const ScanArgs& a, size_t tid) {
     for (size_t i = lo; i < hi; ++i) {
         uint32_t v = a.counts[i];
         a.offsets[i] = run;
-        a.cursor[i] = run;
+        if (a.cursor) a.cursor[i] = run;
         run += v;
     }
 }
@@ -174,34 +174,127 @@ MB_K_MSM_G1(scan_top, ScanArgs, scan_top_body, 32)
 MB_K_MSM_G1(scan_write, ScanArgs, scan_write_body, 128)
 
 // ---------------------------------------------------------------------------
-// 4: bucket accumulation (the hot kernel)
+// 3b: tasks.  A bucket's entry list is cut into segments of at most SEG_LEN
+// entries; one thread accumulates one segment and the (few) partial sums of a
+// split bucket are added afterwards.  No single bucket can serialise the
+// launch: with merged windows the top, partly filled window concentrates its
+// digits on a handful of buckets, and real witnesses repeat small values.
+// Tasks are handed to threads in descending length (a counting sort), so the
+// 32 lanes of a warp run equal trip counts and the long tasks start first.
+// ---------------------------------------------------------------------------
+static const uint32_t SEG_LEN = 128;
+static const uint32_t ORDER_CAP = SEG_LEN + 1;
+struct SegArgs {
+    size_t nthreads;          // buckets
+    const uint32_t* counts;   // entries per bucket
+    const uint32_t* offsets;  // first entry of each bucket
+    uint32_t* nseg;           // segments per bucket (>= 1)
+    const uint32_t* seg_off;  // exclusive scan of nseg
+    uint32_t* task_bucket;    // per task
+    uint32_t* task_start;     // per task: first entry
+    uint32_t* task_len;       // per task: entries
+    uint32_t* ntasks;         // total number of tasks
+};
+MB_HD void seg_count_body(const SegArgs& a, size_t tid) {
+    uint32_t n = a.counts[tid];
+    a.nseg[tid] = n == 0 ? 1u : (n + SEG_LEN - 1) / SEG_LEN;
+}
+MB_HD void seg_fill_body(const SegArgs& a, size_t tid) {
+    uint32_t n = a.counts[tid], ns = a.nseg[tid], t0 = a.seg_off[tid], e0 = a.offsets[tid];
+    for (uint32_t j = 0; j < ns; ++j) {
+        uint32_t done = j * SEG_LEN;
+        a.task_bucket[t0 + j] = (uint32_t)tid;
+        a.task_start[t0 + j] = e0 + done;
+        a.task_len[t0 + j] = n - done < SEG_LEN ? n - done : SEG_LEN;
+    }
+    if (tid + 1 == a.nthreads) *a.ntasks = t0 + ns;
+}
+MB_K_MSM_G1(seg_count, SegArgs, seg_count_body, 256)
+MB_K_MSM_G1(seg_fill, SegArgs, seg_fill_body, 256)
+
+struct OrderArgs {
+    size_t nthreads;  // upper bound on tasks (hist / scatter) or 1 (scan)
+    const uint32_t* task_len;
+    const uint32_t* ntasks;
+    uint32_t* hist;   // ORDER_CAP bins, zeroed
+    uint32_t* order;  // task ids, longest first
+};
+MB_HD void order_hist_body(const OrderArgs& a, size_t tid) {
+    if (tid >= *a.ntasks) return;
+    MB_ATOMIC_ADD(&a.hist[SEG_LEN - a.task_len[tid]], 1u);
+}
+MB_HD void order_scan_body(const OrderArgs& a, size_t) {
+    uint32_t run = 0;
+    for (uint32_t i = 0; i < ORDER_CAP; ++i) {
+        uint32_t v = a.hist[i];
+        a.hist[i] = run;
+        run += v;
+    }
+}
+MB_HD void order_scatter_body(const OrderArgs& a, size_t tid) {
+    if (tid >= *a.ntasks) return;
+    uint32_t pos = MB_ATOMIC_ADD(&a.hist[SEG_LEN - a.task_len[tid]], 1u);
+    a.order[pos] = (uint32_t)tid;
+}
+MB_K_MSM_G1(order_hist, OrderArgs, order_hist_body, 256)
+MB_K_MSM_G1(order_scan, OrderArgs, order_scan_body, 32)
+MB_K_MSM_G1(order_scatter, OrderArgs, order_scatter_body, 256)
+
+// ---------------------------------------------------------------------------
+// 4: segment accumulation (the hot kernel)
 // ---------------------------------------------------------------------------
 template <class F>
 struct AccArgs {
-    size_t nthreads;  // buckets
+    size_t nthreads;  // upper bound on tasks
     const Affine<F>* table;
     const uint32_t* entries;
-    const uint32_t* offsets;
-    const uint32_t* counts;
-    XYZZ<F>* buckets;
+    const uint32_t* task_start;
+    const uint32_t* task_len;
+    const uint32_t* order;  // thread -> task
+    const uint32_t* ntasks;
+    XYZZ<F>* partials;      // per task
 };
 template <class F>
 MB_HD void acc_body(const AccArgs<F>& a, size_t tid) {
-    uint32_t n = a.counts[tid];
+    if (tid >= *a.ntasks) return;
+    uint32_t t = a.order[tid];
+    uint32_t n = a.task_len[t];
     XYZZ<F> acc = XYZZ<F>::inf();
-    const uint32_t* e = a.entries + a.offsets[tid];
+    const uint32_t* e = a.entries + a.task_start[t];
     MB_NOUNROLL
     for (uint32_t i = 0; i < n; ++i) {
         uint32_t ent = e[i];
         Affine<F> q = a.table[ent >> 1];
         xyzz_madd(acc, q, (ent & 1) != 0);
     }
-    a.buckets[tid] = acc;
+    a.partials[t] = acc;
 }
 MB_HD void acc_g1_body(const AccArgs<Fp>& a, size_t tid) { acc_body<Fp>(a, tid); }
 MB_HD void acc_g2_body(const AccArgs<Fp2>& a, size_t tid) { acc_body<Fp2>(a, tid); }
 MB_K_MSM_G1(msm_accumulate_g1, AccArgs<Fp>, acc_g1_body, 128)
 MB_K_MSM_G2(msm_accumulate_g2, AccArgs<Fp2>, acc_g2_body, 64)
+
+// bucket sum = sum of its segments' partial sums (one for almost every bucket)
+template <class F>
+struct CombineArgs {
+    size_t nthreads;  // buckets
+    const XYZZ<F>* partials;
+    const uint32_t* seg_off;
+    const uint32_t* nseg;
+    XYZZ<F>* buckets;
+};
+template <class F>
+MB_HD void combine_body(const CombineArgs<F>& a, size_t tid) {
+    uint32_t t0 = a.seg_off[tid], ns = a.nseg[tid];
+    XYZZ<F> acc = a.partials[t0];
+    MB_NOUNROLL
+    for (uint32_t j = 1; j < ns; ++j) xyzz_add_cold(acc, a.partials[t0 + j]);
+    a.buckets[tid] = acc;
+}
+MB_HD void combine_g1_body(const CombineArgs<Fp>& a, size_t tid) { combine_body<Fp>(a, tid); }
+MB_HD void combine_g2_body(const CombineArgs<Fp2>& a, size_t tid) { combine_body<Fp2>(a, tid); }
+MB_K_RED_G1(msm_combine_g1, CombineArgs<Fp>, combine_g1_body, 128)
+MB_K_RED_G2(msm_combine_g2, CombineArgs<Fp2>, combine_g2_body, 64)
 
 // ---------------------------------------------------------------------------
 // 5: reduction  W = sum_i i * X_i  (+ plain sum of the ones buckets)
@@ -262,8 +355,8 @@ MB_HD void red_body(const RedArgs<F>& a, size_t tid) {
 }
 MB_HD void red_g1_body(const RedArgs<Fp>& a, size_t tid) { red_body<Fp>(a, tid); }
 MB_HD void red_g2_body(const RedArgs<Fp2>& a, size_t tid) { red_body<Fp2>(a, tid); }
-MB_K_MSM_G1(msm_reduce_g1, RedArgs<Fp>, red_g1_body, 64)
-MB_K_MSM_G2(msm_reduce_g2, RedArgs<Fp2>, red_g2_body, 32)
+MB_K_RED_G1(msm_reduce_g1, RedArgs<Fp>, red_g1_body, 64)
+MB_K_RED_G2(msm_reduce_g2, RedArgs<Fp2>, red_g2_body, 32)
 
 // Horner over per-window results (non-precomputed tables only):
 // out[inst] = sum_w 2^(c w) * R[inst][w]
@@ -289,14 +382,15 @@ MB_HD void horner_body(const HornerArgs<F>& a, size_t tid) {
 }
 MB_HD void horner_g1_body(const HornerArgs<Fp>& a, size_t tid) { horner_body<Fp>(a, tid); }
 MB_HD void horner_g2_body(const HornerArgs<Fp2>& a, size_t tid) { horner_body<Fp2>(a, tid); }
-MB_K_MSM_G1(msm_horner_g1, HornerArgs<Fp>, horner_g1_body, 32)
-MB_K_MSM_G2(msm_horner_g2, HornerArgs<Fp2>, horner_g2_body, 32)
+MB_K_RED_G1(msm_horner_g1, HornerArgs<Fp>, horner_g1_body, 32)
+MB_K_RED_G2(msm_horner_g2, HornerArgs<Fp2>, horner_g2_body, 32)
 
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
 struct MsmScratch {
-    DevBuf counts, offsets, cursor, partial, entries, buckets, lx[2], lp[2];
+    DevBuf counts, offsets, cursor, partial, entries, buckets, lx[2], lp[2], order, ohist;
+    DevBuf nseg, seg_off, task_bucket, task_start, task_len, ntasks, partials;
 };
 
 struct MsmProfile {  // optional CUDA-event timing of the accumulate kernel
@@ -315,6 +409,12 @@ template <>
 inline void launch_acc<Fp>(const AccArgs<Fp>& a, cudaStream_t s) { launch_msm_accumulate_g1(a, s); }
 template <>
 inline void launch_acc<Fp2>(const AccArgs<Fp2>& a, cudaStream_t s) { launch_msm_accumulate_g2(a, s); }
+template <class F>
+inline void launch_combine(const CombineArgs<F>& a, cudaStream_t s);
+template <>
+inline void launch_combine<Fp>(const CombineArgs<Fp>& a, cudaStream_t s) { launch_msm_combine_g1(a, s); }
+template <>
+inline void launch_combine<Fp2>(const CombineArgs<Fp2>& a, cudaStream_t s) { launch_msm_combine_g2(a, s); }
 template <class F>
 inline void launch_red(const RedArgs<F>& a, cudaStream_t s);
 template <>
@@ -372,13 +472,66 @@ void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t po
 
     launch_msm_scatter(da, s);
 
+    // tasks: segments of at most SEG_LEN entries, longest first
+    size_t max_tasks = nbuckets + max_entries / SEG_LEN + 1;
+    if (max_tasks >= (1ull << 32)) fail(MB200_EINVAL, "too many buckets%s (%ld)", "", (long)nbuckets);
+    w.nseg.ensure(nbuckets * 4);
+    w.seg_off.ensure(nbuckets * 4);
+    w.task_bucket.ensure(max_tasks * 4);
+    w.task_start.ensure(max_tasks * 4);
+    w.task_len.ensure(max_tasks * 4);
+    w.order.ensure(max_tasks * 4);
+    w.ntasks.ensure(4);
+    w.ohist.ensure(ORDER_CAP * 4);
+    w.partials.ensure(max_tasks * sizeof(XYZZ<F>));
+    SegArgs ga;
+    ga.nthreads = nbuckets;
+    ga.counts = w.counts.as<uint32_t>();
+    ga.offsets = w.offsets.as<uint32_t>();
+    ga.nseg = w.nseg.as<uint32_t>();
+    ga.seg_off = w.seg_off.as<uint32_t>();
+    ga.task_bucket = w.task_bucket.as<uint32_t>();
+    ga.task_start = w.task_start.as<uint32_t>();
+    ga.task_len = w.task_len.as<uint32_t>();
+    ga.ntasks = w.ntasks.as<uint32_t>();
+    launch_seg_count(ga, s);
+    ScanArgs sg;
+    sg.counts = w.nseg.as<uint32_t>();
+    sg.offsets = w.seg_off.as<uint32_t>();
+    sg.cursor = nullptr;
+    sg.partial = w.partial.as<uint32_t>();
+    sg.n = nbuckets;
+    sg.chunk = SCAN_CHUNK;
+    sg.nthreads = nchunks;
+    launch_scan_sum(sg, s);
+    sg.nthreads = 1;
+    launch_scan_top(sg, s);
+    sg.nthreads = nchunks;
+    launch_scan_write(sg, s);
+    launch_seg_fill(ga, s);
+
+    dev_memset(w.ohist.p, 0, ORDER_CAP * 4, s);
+    OrderArgs oa;
+    oa.task_len = w.task_len.as<uint32_t>();
+    oa.ntasks = w.ntasks.as<uint32_t>();
+    oa.hist = w.ohist.as<uint32_t>();
+    oa.order = w.order.as<uint32_t>();
+    oa.nthreads = max_tasks;
+    launch_order_hist(oa, s);
+    oa.nthreads = 1;
+    launch_order_scan(oa, s);
+    oa.nthreads = max_tasks;
+    launch_order_scatter(oa, s);
+
     AccArgs<F> aa;
-    aa.nthreads = nbuckets;
+    aa.nthreads = max_tasks;
     aa.table = (const Affine<F>*)k.table;
     aa.entries = w.entries.as<uint32_t>();
-    aa.offsets = w.offsets.as<uint32_t>();
-    aa.counts = w.counts.as<uint32_t>();
-    aa.buckets = w.buckets.as<XYZZ<F>>();
+    aa.task_start = w.task_start.as<uint32_t>();
+    aa.task_len = w.task_len.as<uint32_t>();
+    aa.order = w.order.as<uint32_t>();
+    aa.ntasks = w.ntasks.as<uint32_t>();
+    aa.partials = w.partials.as<XYZZ<F>>();
 #ifndef MB200_EMU
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_msm_profile.enabled) {
@@ -401,6 +554,13 @@ void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t po
         cudaEventDestroy(e1);
     }
 #endif
+    CombineArgs<F> ca;
+    ca.nthreads = nbuckets;
+    ca.partials = w.partials.as<XYZZ<F>>();
+    ca.seg_off = w.seg_off.as<uint32_t>();
+    ca.nseg = w.nseg.as<uint32_t>();
+    ca.buckets = w.buckets.as<XYZZ<F>>();
+    launch_combine<F>(ca, s);
 
     // reduction levels
     uint32_t jobs = n_inst * k.nsets;

@@ -354,11 +354,15 @@ inline Params* params_load(const uint8_t* buf, size_t len, const uint8_t* a_aux_
 // ---------------------------------------------------------------------------
 // prove
 // ---------------------------------------------------------------------------
-struct ProveCtx {  // one in-flight chunk: a stream and its scratch
-    cudaStream_t stream = 0;
+struct ProveCtx {  // one in-flight chunk: its streams and scratch
+    cudaStream_t stream = 0;      // copies, NTT, H+L MSM, assembly
+    cudaStream_t side[3] = {0, 0, 0};  // A, B1, B2 MSMs: they need only the staged witness, not the NTT
     DevBuf abc, w0, w1, w2, w3, pool, flag, res_hl, res_a, res_b1, res_b2, cmul, proofs;
-    MsmScratch msm;
+    MsmScratch msm, msm_side[3];
     bool have_stream = false;
+#ifndef MB200_EMU
+    cudaEvent_t ev_inputs = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
+#endif
 };
 
 struct ProveInputs {  // host or device pointers, selected by `on_device`
@@ -414,14 +418,28 @@ inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, siz
     FillOneArgs fo{count, x.pool.as<uint32_t>(), P.pool_stride, P.idx_one};
     launch_pool_fill_one(fo, s);
 
+    const uint32_t* pl = x.pool.as<uint32_t>();
+    // fork: the A / B1 / B2 queries read aux, inputs, r, s only, so they run on
+    // side streams next to the NTT pipeline and the H+L query; their
+    // latency-bound reduction tails overlap the other streams' heavy kernels.
+#ifndef MB200_EMU
+    MB_CUDA(cudaEventRecord(x.ev_inputs, s));
+    for (int i = 0; i < 3; ++i) MB_CUDA(cudaStreamWaitEvent(x.side[i], x.ev_inputs, 0));
+#endif
+    msm_run<Fp>(P.k_a, count, pl, P.pool_stride, x.res_a.as<G1XYZZ>(), x.msm_side[0], x.side[0]);
+    msm_run<Fp>(P.k_b1, count, pl, P.pool_stride, x.res_b1.as<G1XYZZ>(), x.msm_side[1], x.side[1]);
+    msm_run<Fp2>(P.k_b2, count, pl, P.pool_stride, x.res_b2.as<G2XYZZ>(), x.msm_side[2], x.side[2]);
+
     h_pipeline(P.dom, count, (uint32_t)rows, x.abc.as<Fr>(), rows, x.pool.as<Fr>(), P.pool_stride, x.w0.as<Fr>(),
                x.w1.as<Fr>(), x.w2.as<Fr>(), x.w3.as<Fr>(), s);
-
-    const uint32_t* pl = x.pool.as<uint32_t>();
     msm_run<Fp>(P.k_hl, count, pl, P.pool_stride, x.res_hl.as<G1XYZZ>(), x.msm, s);
-    msm_run<Fp>(P.k_a, count, pl, P.pool_stride, x.res_a.as<G1XYZZ>(), x.msm, s);
-    msm_run<Fp>(P.k_b1, count, pl, P.pool_stride, x.res_b1.as<G1XYZZ>(), x.msm, s);
-    msm_run<Fp2>(P.k_b2, count, pl, P.pool_stride, x.res_b2.as<G2XYZZ>(), x.msm, s);
+    // join
+#ifndef MB200_EMU
+    for (int i = 0; i < 3; ++i) {
+        MB_CUDA(cudaEventRecord(x.ev_side[i], x.side[i]));
+        MB_CUDA(cudaStreamWaitEvent(s, x.ev_side[i], 0));
+    }
+#endif
 
     CmulArgs ca{(size_t)count * 2, x.res_a.as<G1XYZZ>(), x.res_b1.as<G1XYZZ>(), pl, P.pool_stride, P.idx_r, P.idx_s,
                 x.cmul.as<G1XYZZ>()};

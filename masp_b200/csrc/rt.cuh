@@ -180,6 +180,16 @@ inline void stream_sync(cudaStream_t) {}
 #else
 #define MB_K_MISC(name, Args, body, BLOCK) MB_KERNEL_DECL(name, Args)
 #endif
+#ifdef MB_DEFINE_RED_G1
+#define MB_K_RED_G1(name, Args, body, BLOCK) MB_KERNEL_DEF(name, Args, body, BLOCK)
+#else
+#define MB_K_RED_G1(name, Args, body, BLOCK) MB_KERNEL_DECL(name, Args)
+#endif
+#ifdef MB_DEFINE_RED_G2
+#define MB_K_RED_G2(name, Args, body, BLOCK) MB_KERNEL_DEF(name, Args, body, BLOCK)
+#else
+#define MB_K_RED_G2(name, Args, body, BLOCK) MB_KERNEL_DECL(name, Args)
+#endif
 
 // RAII device buffer
 struct DevBuf {

@@ -32,6 +32,10 @@ def test_msm(emu, oracle):
     for n in (0, 1, 5, 40, 300):
         sc = ib(rand_scalars(n, n))
         assert emu.msm_g1(bases[:96 * n], sc, n) == oracle.msm_g1(bases[:96 * n], sc, n), n
+    # heavy buckets: every scalar equal -> one bucket per window holds all 300 entries (3 segments)
+    for val in (7, syn.R_INT - 1, 1, (1 << 200) + 5):
+        sc = ib([val] * 300)
+        assert emu.msm_g1(bases, sc, 300) == oracle.msm_g1(bases, sc, 300), val
     b2 = oracle.g2_gen_mul(syn.limbs_to_bytes(logs[:12]), 12)
     sc = ib(rand_scalars(12, 77))
     assert emu.msm_g2(b2, sc, 12) == oracle.msm_g2(b2, sc, 12)

@@ -90,6 +90,19 @@ def test_msm_g1_special_bases(gpu, oracle):
         assert gpu.msm_g1(b, ib(scalars), len(seq)) == oracle.msm_g1(b, ib(scalars), len(seq)), scalars
 
 
+def test_msm_heavy_buckets(gpu, oracle):
+    # every scalar equal: one bucket per window receives all n entries and is cut into segments
+    n = 3000
+    logs, bases = _g1_bases(oracle, n)
+    for val in (7, R - 1, 1, (1 << 200) + 5):
+        sc = ib([val] * n)
+        assert gpu.msm_g1(bases, sc, n) == oracle.msm_g1(bases, sc, n), val
+    l2 = syn.fr_uniform(syn.MASTER_SEED, 15, 400)
+    b2 = oracle.g2_gen_mul(syn.limbs_to_bytes(l2), 400)
+    sc = ib([12345] * 400)
+    assert gpu.msm_g2(b2, sc, 400) == oracle.msm_g2(b2, sc, 400)
+
+
 def syn_p():
     return 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
 
@@ -191,7 +204,7 @@ def test_prove_spend_shape_batch(gpu, oracle):
     again = gpu.create_proof_batch([assignment(gpu, w) for w in ws], P, [w["r"] for w in ws], [w["s"] for w in ws])
     assert again == proofs
     assert len(set(proofs)) == len(proofs)
-    gpu.set_option("chunk", 16)
+    gpu.set_option("chunk", 64)
 
 
 def test_prove_all_zero_and_all_one_witness(gpu, oracle):
