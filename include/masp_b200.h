@@ -126,6 +126,9 @@ int mb200_get_counter(const char* name, double* value);
 int mb200_selftest(void);
 /* throughput of Fp Montgomery multiplications on the whole chip, per second */
 int mb200_bench_fpmul(double* muls_per_second);
+/* single-warp latency, nanoseconds per dependent operation: mode 0 inlined Fp
+ * multiply, 1 out-of-line Fp multiply, 2 XYZZ doubling, 3 XYZZ addition */
+int mb200_bench_latency(int mode, double* ns_per_op);
 
 const char* mb200_strerror(int code);
 const char* mb200_last_error(void);

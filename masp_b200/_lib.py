@@ -15,7 +15,7 @@ SYMBOLS = [
     "mb200_params_synth_size", "mb200_params_synthesize", "mb200_synth_points", "mb200_prove_batch",
     "mb200_prove_batch_device", "mb200_msm_g1", "mb200_msm_g2", "mb200_g1_bases_upload", "mb200_dev_free",
     "mb200_msm_g1_partial", "mb200_g1_sum_partials", "mb200_ntt", "mb200_h_coeffs", "mb200_fr_mul",
-    "mb200_fr_mul_device", "mb200_set_option", "mb200_get_counter", "mb200_selftest", "mb200_bench_fpmul",
+    "mb200_fr_mul_device", "mb200_set_option", "mb200_get_counter", "mb200_selftest", "mb200_bench_fpmul", "mb200_bench_latency",
     "mb200_strerror", "mb200_last_error",
 ]
 
@@ -61,6 +61,7 @@ def bind(path):
     L.mb200_get_counter.argtypes = [u8p, c.POINTER(c.c_double)]
     L.mb200_selftest.argtypes = []
     L.mb200_bench_fpmul.argtypes = [c.POINTER(c.c_double)]
+    L.mb200_bench_latency.argtypes = [c.c_int, c.POINTER(c.c_double)]
     L.mb200_strerror.argtypes = [c.c_int]
     L.mb200_strerror.restype = u8p
     L.mb200_last_error.argtypes = []

@@ -595,6 +595,37 @@ int mb200_bench_fpmul(double* muls_per_second) {
     MB_API_END
 }
 
+int mb200_bench_latency(int mode, double* ns_per_op) {
+    MB_API_BEGIN
+    require_init();
+    if (!ns_per_op || mode < 0 || mode > 3) fail(MB200_EINVAL, "bad argument%s", "");
+#ifndef MB200_EMU
+    LatencyArgs a;
+    a.nthreads = 32;
+    a.iters = 2000;
+    a.mode = (uint32_t)mode;
+    a.g1 = g1_generator_host();
+    DevBuf sink(32 * sizeof(Fp));
+    a.sink = sink.as<Fp>();
+    launch_latency_kernel(a, g.main);
+    cudaEvent_t e0, e1;
+    MB_CUDA(cudaEventCreate(&e0));
+    MB_CUDA(cudaEventCreate(&e1));
+    MB_CUDA(cudaEventRecord(e0, g.main));
+    launch_latency_kernel(a, g.main);
+    MB_CUDA(cudaEventRecord(e1, g.main));
+    MB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    MB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ns_per_op = (double)ms * 1e6 / a.iters;
+#else
+    *ns_per_op = 0;
+#endif
+    MB_API_END
+}
+
 const char* mb200_strerror(int code) {
     switch (code) {
         case MB200_OK: return "ok";

@@ -161,14 +161,26 @@ MB_COLD Affine<F> xyzz_to_affine(const XYZZ<F>& p) {
     return {F::mul(p.x, izz), F::mul(p.y, izzz)};
 }
 
-// k * P for a 256-bit plain little-endian scalar (8 limbs), MSB first
+// k * P for a 256-bit plain little-endian scalar (8 limbs): fixed 4-bit
+// windows, MSB first (256 doublings + at most 64 additions, no divergence
+// on the scalar's bits beyond skipping zero digits)
 template <class F>
 MB_COLD XYZZ<F> xyzz_mul(const XYZZ<F>& p, const uint32_t* k) {
+    XYZZ<F> tab[16];
+    tab[0] = XYZZ<F>::inf();
+    tab[1] = p;
+    MB_NOUNROLL
+    for (int j = 2; j < 16; ++j) {
+        tab[j] = tab[j - 1];
+        xyzz_add_cold(tab[j], p);
+    }
     XYZZ<F> acc = XYZZ<F>::inf();
     MB_NOUNROLL
-    for (int i = 255; i >= 0; --i) {
-        acc = xyzz_dbl_cold(acc);
-        if ((k[i >> 5] >> (i & 31)) & 1) xyzz_add_cold(acc, p);
+    for (int w = 63; w >= 0; --w) {
+        MB_NOUNROLL
+        for (int d = 0; d < 4; ++d) acc = xyzz_dbl_cold(acc);
+        uint32_t digit = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
+        if (digit) xyzz_add_cold(acc, tab[digit]);
     }
     return acc;
 }

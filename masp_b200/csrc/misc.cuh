@@ -101,14 +101,36 @@ struct FpMulBenchArgs {
 MB_HD void fpmul_bench_body(const FpMulBenchArgs& a, size_t tid) {
     Fp x = st_rand<Fp>(1, tid), y = st_rand<Fp>(2, tid), z = st_rand<Fp>(3, tid), w = st_rand<Fp>(4, tid);
     for (uint32_t i = 0; i < a.iters; ++i) {
-        x = Fp::mul(x, y);
-        y = Fp::mul(y, z);
-        z = Fp::mul(z, w);
-        w = Fp::mul(w, x);
+        x = Fp::mul_inline(x, y);  // the inlined multiplier of the hot kernel, not the out-of-line copy
+        y = Fp::mul_inline(y, z);
+        z = Fp::mul_inline(z, w);
+        w = Fp::mul_inline(w, x);
     }
     if (x.v[0] == 0x12345 && y.v[1] == 7) a.sink[tid] = Fp::add(Fp::add(x, y), Fp::add(z, w));
 }
 MB_K_MISC(fpmul_bench, FpMulBenchArgs, fpmul_bench_body, 256)
+
+// single-warp latency of dependent operations (mode 0: inlined multiply,
+// 1: out-of-line multiply, 2: out-of-line XYZZ doubling, 3: out-of-line XYZZ add)
+struct LatencyArgs {
+    size_t nthreads;
+    Fp* sink;
+    uint32_t iters, mode;
+    G1Affine g1;
+};
+MB_HD void latency_body(const LatencyArgs& a, size_t tid) {
+    Fp x = st_rand<Fp>(1, tid), y = st_rand<Fp>(2, tid);
+    G1XYZZ p = G1XYZZ::from_affine(a.g1), q = xyzz_dbl_cold(p);
+    MB_NOUNROLL
+    for (uint32_t i = 0; i < a.iters; ++i) {
+        if (a.mode == 0) x = Fp::mul_inline(x, y);
+        else if (a.mode == 1) x = Fp::mul(x, y);
+        else if (a.mode == 2) p = xyzz_dbl_cold(p);
+        else xyzz_add_cold(p, q);
+    }
+    a.sink[tid] = Fp::add(x, p.x);
+}
+MB_K_MISC(latency_kernel, LatencyArgs, latency_body, 32)
 
 struct IotaArgs {
     size_t nthreads;

@@ -395,3 +395,10 @@ def bench_fpmul():
     v = ctypes.c_double()
     check(_lib.lib().mb200_bench_fpmul(ctypes.byref(v)))
     return v.value
+
+
+def bench_latency(mode):
+    _ensure_init()
+    v = ctypes.c_double()
+    check(_lib.lib().mb200_bench_latency(mode, ctypes.byref(v)))
+    return v.value

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""BASELINE configs 2 and 4 on one or more GPUs (one process per GPU).
+
+  --mode convert : Convert-shape proofs, `--per-gpu` per rank (config 2: 128 per GPU on 8 GPUs)
+  --mode mixed   : `--tx` transactions per rank of (2 Spend + 2 Output + 1 Convert) (config 4),
+                   work ordered longest circuit first (masp_b200.sharding.longest_first_queue)
+
+Reports end-to-end proofs/s (and tx/s) through mb200_prove_batch with host
+buffers, and compares a sample with the oracle when --check is given.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from masp_b200 import sharding, synthetic as syn  # noqa: E402
+import masp_b200.prover as pv  # noqa: E402
+
+
+def batch_for(shape, n, first):
+    """n witnesses as concatenated host byte strings (c = a*b on the device)."""
+    ws = [syn.witness(shape, first + i, pv.fr_mul) for i in range(n)]
+    cat = lambda k: b"".join(w[k] for w in ws)
+    return {k: cat(k) for k in ("a", "b", "c", "inputs", "aux", "r", "s")}, ws
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="mixed", choices=["mixed", "convert"])
+    ap.add_argument("--tx", type=int, default=16)
+    ap.add_argument("--per-gpu", type=int, default=128)
+    ap.add_argument("--check", type=int, default=0, help="proofs per circuit to compare with the oracle on rank 0")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pv.init(local)
+    counts = {"convert": args.per_gpu} if args.mode == "convert" else \
+        {"spend": 2 * args.tx, "output": 2 * args.tx, "convert": args.tx}
+    order = []
+    for c, _ in sharding.longest_first_queue(counts):
+        if c not in order:
+            order.append(c)
+    keys, params, data = {}, {}, {}
+    for c in order:
+        sh = syn.SHAPES[c]
+        keys[c] = pv.params_synthesize(sh)
+        params[c] = pv.Parameters.read(keys[c], sh.densities())
+        data[c] = batch_for(sh, counts[c], rank * counts[c])
+    # warm-up (allocations, tables in L2)
+    for c in order:
+        d, _ = data[c]
+        pv.prove_batch_raw(params[c], min(4, counts[c]), syn.SHAPES[c].rows, d["a"], d["b"], d["c"], d["inputs"], d["aux"], d["r"], d["s"])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    proofs = {}
+    for c in order:
+        d, _ = data[c]
+        proofs[c] = pv.prove_batch_raw(params[c], counts[c], syn.SHAPES[c].rows, d["a"], d["b"], d["c"], d["inputs"],
+                                       d["aux"], d["r"], d["s"])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    if rank == 0:
+        total = world * sum(counts.values())
+        out = {"config": args.mode, "n_gpus": world, "proofs": total, "seconds": dt, "proofs_per_s": total / dt,
+               "per_gpu": counts}
+        if args.mode == "mixed":
+            out["tx_per_s"] = world * args.tx / dt
+        if args.check:
+            from oracle import c_oracle as co
+            okay = 0
+            for c in order:
+                sh = syn.SHAPES[c]
+                P = co.Params(keys[c], sh.n_aux, *sh.densities())
+                for i, w in enumerate(data[c][1][:args.check]):
+                    want = P.prove(sh.rows, w["a"], w["b"], w["c"], w["inputs"], w["aux"], w["r"], w["s"])
+                    okay += want == proofs[c][192 * i:192 * (i + 1)]
+            out["byte_identical_to_oracle"] = "%d/%d" % (okay, args.check * len(order))
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,22 @@
+#!/usr/bin/env python
+"""Latency of one proof at a time (how the reference's SaplingBuilder calls the prover)."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import masp_b200.prover as pv  # noqa: E402
+from masp_b200 import synthetic as syn  # noqa: E402
+
+pv.init(0)
+for name in sys.argv[1:] or ["output", "convert", "spend"]:
+    sh = syn.SHAPES[name]
+    P = pv.Parameters.read(pv.params_synthesize(sh), sh.densities())
+    w = syn.witness(sh, 0, pv.fr_mul)
+    a = pv.ProvingAssignment(w["a"], w["b"], w["c"], w["inputs"], w["aux"])
+    for i in range(3):
+        t0 = time.perf_counter()
+        pv.create_proof(a, P, w["r"], w["s"])
+        print(name, "wall %.1f ms" % ((time.perf_counter() - t0) * 1e3),
+              "device %.1f ms" % (pv.get_counter("last_batch_us") / 1e3), flush=True)
+    del P
