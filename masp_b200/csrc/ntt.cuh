@@ -217,12 +217,17 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
                     size_t dst_stride, Fr* tmp0, Fr* tmp1, cudaStream_t s) {
     uint32_t n = 1u << d.log_n;
     uint32_t left = d.log_n, ns = 1;
+    static const uint32_t max_k = []() {
+        const char* v = getenv("MB200_NTT_RADIX_LOG");
+        uint32_t k = v && *v ? (uint32_t)strtoul(v, nullptr, 10) : 3;
+        return k < 1 ? 1u : (k > 3 ? 3u : k);
+    }();
     const Fr* cur = src;
     size_t cur_stride = src_stride;
     int flip = 0;
     bool first = true;
     while (left) {
-        uint32_t K = left >= 3 ? 3 : left;
+        uint32_t K = left >= max_k ? max_k : left;
         bool last = left == K;
         NttArgs a;
         a.nthreads = (size_t)batch * (n >> K);

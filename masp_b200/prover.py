@@ -279,7 +279,8 @@ class LocalTxProver:
         for params, group in ((self.spend_params, spends), (self.convert_params, converts),
                               (self.output_params, outputs)):
             group = list(group)
-            res.append(create_proof_batch(group, params, [rng() for _ in group], [rng() for _ in group]))
+            pairs = [(rng(), rng()) for _ in group]  # r then s for each description, in order
+            res.append(create_proof_batch(group, params, [p[0] for p in pairs], [p[1] for p in pairs]))
         return tuple(res)
 
 

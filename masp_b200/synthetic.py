@@ -233,6 +233,11 @@ def tiny_shape(name="tiny", n_constraints=200, n_inputs=4):
     return Shape(name, n_constraints, n_inputs, 40, 15, 3, 2, 30, 20, 6, 25)
 
 
+def micro_shape(name="micro", n_constraints=56, n_inputs=3):
+    """The smallest shape with every class populated (host-emulated device tests)."""
+    return Shape(name, n_constraints, n_inputs, 9, 4, 2, 1, 7, 5, 2, 6)
+
+
 def witness(shape, proof_index, fr_mul, seed=MASTER_SEED):
     """Synthetic evaluation vectors for one proof:
     a_i, b_i uniform, c_i = a_i * b_i for i < rows; aux boolean/full-width by

@@ -31,7 +31,7 @@ def _worker(rank, world, port, q):
         got = sharding.split_msm_g1(pv, bases, sc, n)
         ok_msm = got == co.msm_g1(bases, sc, n)
         # proof sharding, uneven split (5 proofs over 2 ranks)
-        sh = syn.tiny_shape()
+        sh = syn.micro_shape()
         kb = co.params_from_logs(syn.key_logs(sh))
         dens = sh.densities()
         P = pv.Parameters.read(kb, dens)

@@ -46,7 +46,7 @@ def test_msm(emu, oracle):
 
 @pytest.mark.slow
 def test_prove_batch_chunked(emu, oracle):
-    sh = syn.tiny_shape()
+    sh = syn.micro_shape()
     kb = emu.params_synthesize(sh)
     assert kb == oracle.params_from_logs(syn.key_logs(sh))
     dens = sh.densities()
@@ -63,3 +63,30 @@ def test_prove_batch_chunked(emu, oracle):
     with pytest.raises(emu.Mb200Error) as e:
         emu.create_proof(assignment(emu, w), P, w["r"], w["s"])
     assert e.value.code == -6
+
+
+@pytest.mark.slow
+def test_local_tx_prover_surface(emu, oracle):
+    """LocalTxProver::from_bytes / prove_bundle, and a parameter stream followed
+    by transcript bytes as in the real .params files (masp_proofs/src/lib.rs:343-388)."""
+    sh = syn.micro_shape()
+    kb = oracle.params_from_logs(syn.key_logs(sh))
+    tail = bytes(range(256)) * 5
+    dens = {"spend": sh.densities(), "output": sh.densities(), "convert": sh.densities()}
+    with pytest.raises(emu.ParameterError):  # BLAKE2b of a synthetic file cannot match the pinned hash
+        emu.LocalTxProver.from_bytes(kb + tail, kb + tail, kb + tail, dens)
+    prover = emu.LocalTxProver.from_bytes(kb + tail, kb, kb + tail, dens, verify_hashes=False)
+    assert prover.spend_params.consumed == len(kb)
+    ws = [syn.witness(sh, i, oracle.fr_mul) for i in range(3)]
+    fixed = iter([int.from_bytes(w[k], "little") for w in ws for k in ("r", "s")])
+    # rng is called r, s per proof in order within each circuit group
+    spends, converts, outputs = [assignment(emu, ws[0])], [assignment(emu, ws[1])], [assignment(emu, ws[2])]
+    rs = {0: (ws[0]["r"], ws[0]["s"]), 1: (ws[1]["r"], ws[1]["s"]), 2: (ws[2]["r"], ws[2]["s"])}
+    seq = [rs[0][0], rs[0][1], rs[1][0], rs[1][1], rs[2][0], rs[2][1]]
+    it = iter(seq)
+    got = prover.prove_bundle(spends, converts, outputs, rng=lambda: next(it))
+    want = oracle_proofs(oracle, kb, sh, sh.densities(), ws)
+    assert [got[0][0], got[1][0], got[2][0]] == want
+    # create_random_proof draws r, s itself: two calls must differ, both must be 192 bytes
+    p1, p2 = prover.spend_proof(spends[0]), prover.spend_proof(spends[0])
+    assert len(p1) == len(p2) == 192 and p1 != p2
