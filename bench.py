@@ -211,6 +211,7 @@ def main():
     t_setup = time.perf_counter() - t_setup
     rows = shape.rows
     out_pinned = torch.empty(B * 192, dtype=torch.uint8).pin_memory()
+    out_ring = [out_pinned, torch.empty(B * 192, dtype=torch.uint8).pin_memory()]
 
     def barrier():
         torch.cuda.synchronize()
@@ -227,6 +228,18 @@ def main():
         pv.prove_batch_raw(params, B, rows, host["a"], host["b"], host["c"], host["inputs"], host["aux"], host["r"],
                            host["s"], device=False, out=out_pinned)
 
+    def run_steps(k_steps, src, device):
+        """K steps streamed through mb200_prove_submit / mb200_prove_wait with at
+        most two batches in flight: the tail of step k overlaps the head of k+1."""
+        tickets = []
+        for k in range(k_steps):
+            tickets.append(pv.prove_submit(params, B, rows, src["a"], src["b"], src["c"], src["inputs"], src["aux"],
+                                           src["r"], src["s"], out_ring[k % 2], device=device))
+            if len(tickets) > 1:
+                pv.prove_wait(tickets.pop(0))
+        while tickets:
+            pv.prove_wait(tickets.pop(0))
+
     def max_over_ranks(x):
         if world == 1:
             return x
@@ -234,35 +247,34 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    dev_ms_sync = 0.0
     for _ in range(args.warmup):
-        step_device()
+        dev_ms_sync = step_device()
+    proofs_dev = bytes(out_pinned.numpy())
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = pv.get_counter("launches")
     barrier()
     t0 = time.perf_counter()
-    dev_ms = 0.0
-    for _ in range(args.steps):
-        dev_ms += step_device()
+    run_steps(args.steps, dev, True)
     barrier()
     wall = time.perf_counter() - t0
     launches = pv.get_counter("launches") - launches0
     wall = max_over_ranks(wall)
-    dev_ms = max_over_ranks(dev_ms)
-    proofs_dev = bytes(out_pinned.numpy())
+    dev_ms = max_over_ranks(dev_ms_sync) * args.steps
+    assert bytes(out_ring[(args.steps - 1) % 2].numpy()) == proofs_dev, "streamed and synchronous calls disagree"
 
     # end to end: pinned host buffers in, proofs out, copies inside the timed region
     step_host()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
+    run_steps(args.steps, host, False)
     barrier()
     wall_e2e = max_over_ranks(time.perf_counter() - t0)
     if rank == 0:
         sampler.stop_flag = True
-    assert bytes(out_pinned.numpy()) == proofs_dev, "host-buffer and device-buffer paths disagree"
+    assert bytes(out_ring[(args.steps - 1) % 2].numpy()) == proofs_dev, "host-buffer and device-buffer paths disagree"
 
     # roofline of the dominant kernel (G1/G2 bucket accumulation), timed live with CUDA events per launch
     pv.set_option("profile", 1)
@@ -293,7 +305,7 @@ def main():
     line = {
         "metric": "spend_proofs_per_sec" if shape.name == "spend" else shape.name + "_proofs_per_sec",
         "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "device_ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+        "ms_per_step": ms_per_step, "device_ms_per_step_unpipelined": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (mod p 381-bit / mod r 255-bit)",
         "data": "synthetic",
         "config": {
@@ -302,6 +314,8 @@ def main():
                                                                     100.0 * shape.n_bool / shape.n_aux),
             "circuit": shape.name, "batch_per_gpu": B, "parallelism": "proof-sharded x%d, no collective" % world,
             "l2": "inputs per step (%.2f GB) are larger than the 126 MB L2" % (h2d / 1e9),
+            "pipelining": "steps are streamed (mb200_prove_submit / mb200_prove_wait, <= 2 batches in flight); "
+                          "the timed region is bracketed by barrier + synchronize",
             "window_bits": {"h_l": params.window_hl, "a": params.window_a},
             "table_bytes_hbm": params.table_bytes, "algorithmic_bytes_per_proof": shape.algorithmic_bytes(),
             "setup_s": round(t_setup, 2), "key_synth_and_load_s": round(t_key, 2),

@@ -91,6 +91,18 @@ int mb200_prove_batch_device(const mb200_params* p, size_t n_proofs, size_t rows
                              const void* b_evals, const void* c_evals, const void* inputs, const void* aux,
                              const void* r, const void* s, uint8_t* proofs_out);
 
+/* Streaming form of the two calls above: submit enqueues the whole batch and
+ * returns a ticket without waiting; wait blocks until that batch is done and
+ * its proofs are in proofs_out.  Batches submitted back to back overlap on the
+ * device (the latency-bound tail of one runs under the head of the next).
+ * Input and output buffers must stay valid until wait returns; with host
+ * inputs (on_device = 0) pinned memory is needed for the copies to be
+ * asynchronous.  Tickets must be waited on in any order, each exactly once. */
+int mb200_prove_submit(const mb200_params* p, size_t n_proofs, size_t rows, const void* a_evals, const void* b_evals,
+                       const void* c_evals, const void* inputs, const void* aux, const void* r, const void* s,
+                       int on_device, uint8_t* proofs_out, uint64_t* ticket);
+int mb200_prove_wait(uint64_t ticket);
+
 /* multiexp over arbitrary bases (ec-gpu-gen `multiexp`, full density);
  * result uncompressed.  No table is precomputed on this path. */
 int mb200_msm_g1(const uint8_t* bases_uncompressed, const uint8_t* scalars, size_t n, uint8_t out_uncompressed[96]);

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmasp_b200.so")
 SYMBOLS = [
     "mb200_init", "mb200_shutdown", "mb200_params_load", "mb200_params_info", "mb200_params_free",
     "mb200_params_synth_size", "mb200_params_synthesize", "mb200_synth_points", "mb200_prove_batch",
-    "mb200_prove_batch_device", "mb200_msm_g1", "mb200_msm_g2", "mb200_g1_bases_upload", "mb200_dev_free",
+    "mb200_prove_batch_device", "mb200_prove_submit", "mb200_prove_wait", "mb200_msm_g1", "mb200_msm_g2", "mb200_g1_bases_upload", "mb200_dev_free",
     "mb200_msm_g1_partial", "mb200_g1_sum_partials", "mb200_ntt", "mb200_h_coeffs", "mb200_fr_mul",
     "mb200_fr_mul_device", "mb200_set_option", "mb200_get_counter", "mb200_selftest", "mb200_bench_fpmul", "mb200_bench_latency",
     "mb200_strerror", "mb200_last_error",
@@ -47,6 +47,8 @@ def bind(path):
     L.mb200_synth_points.argtypes = [u64, u32, u64, sz, c.c_int, vp]
     L.mb200_prove_batch.argtypes = [vp, sz, sz] + [vp] * 7 + [vp]
     L.mb200_prove_batch_device.argtypes = [vp, sz, sz] + [vp] * 7 + [vp]
+    L.mb200_prove_submit.argtypes = [vp, sz, sz] + [vp] * 7 + [c.c_int, vp, c.POINTER(u64)]
+    L.mb200_prove_wait.argtypes = [u64]
     L.mb200_msm_g1.argtypes = [vp, vp, sz, vp]
     L.mb200_msm_g2.argtypes = [vp, vp, sz, vp]
     L.mb200_g1_bases_upload.argtypes = [vp, sz, c.POINTER(vp)]

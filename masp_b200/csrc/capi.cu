@@ -125,72 +125,112 @@ static void check_scalars_dev(const Fr* base, size_t per_row, size_t row_stride,
     launch_validate_scalars(va, s);
 }
 
-static int prove_impl(const Params& P, size_t n_proofs, size_t rows, const ProveInputs& in, uint8_t* proofs_out) {
+// One submitted batch: everything needed to finish it later.
+struct Ticket {
+    uint8_t* staged = nullptr;  // pinned: proofs land here
+    uint8_t* out = nullptr;     // caller's buffer
+    size_t n_proofs = 0;
+    DevBuf flag;                // set by the canonical-scalar checks of this batch
+#ifndef MB200_EMU
+    cudaEvent_t ev0 = nullptr;
+    std::vector<cudaEvent_t> ev1;
+#endif
+};
+static std::map<uint64_t, Ticket*> g_tickets;
+static uint64_t g_next_ticket = 1;
+static size_t g_next_ctx = 0;  // chunks go round the contexts across batches, so consecutive batches overlap
+
+static void ticket_destroy(Ticket* t) {
+    if (!t) return;
+#ifndef MB200_EMU
+    if (t->ev0) cudaEventDestroy(t->ev0);
+    for (auto& e : t->ev1)
+        if (e) cudaEventDestroy(e);
+#endif
+    host_free_pinned(t->staged);
+    delete t;
+}
+
+// Enqueue a whole batch on the chunk contexts; no host synchronisation.
+static uint64_t prove_submit(const Params& P, size_t n_proofs, size_t rows, const ProveInputs& in, uint8_t* proofs_out) {
     require_init();
-    if (n_proofs == 0) return MB200_OK;
     if (!in.a || !in.b || !in.c || !in.inputs || !in.aux || !in.r || !in.s || !proofs_out)
         fail(MB200_EINVAL, "null buffer%s", "");
     size_t m = 1;
     while (m < rows) m <<= 1;
     if (rows == 0 || m != P.m)
         fail(MB200_EINVAL, "rows does not match the key's domain%s (key m = %ld)", "", (long)P.m);
-    uint8_t* staged = (uint8_t*)host_alloc_pinned(n_proofs * 192);
+    Ticket* t = new Ticket();
     try {
-        size_t ci = 0;
+        t->n_proofs = n_proofs;
+        t->out = proofs_out;
+        t->staged = (uint8_t*)host_alloc_pinned(n_proofs * 192);
+        t->flag.alloc(4);
+        dev_memset(t->flag.p, 0, 4, g.main);
 #ifndef MB200_EMU
-        // every chunk stream starts after `ev0`; the batch ends at the latest per-stream end event
-        cudaEvent_t ev0;
-        std::vector<cudaEvent_t> ev1(g.ctxs.size());
-        MB_CUDA(cudaEventCreate(&ev0));
-        for (auto& e : ev1) MB_CUDA(cudaEventCreate(&e));
-        MB_CUDA(cudaEventRecord(ev0, g.main));
-        for (auto& x : g.ctxs) MB_CUDA(cudaStreamWaitEvent(x.stream, ev0, 0));
+        // every chunk stream starts after `ev0` (and so after the flag reset)
+        t->ev1.assign(g.ctxs.size(), nullptr);
+        MB_CUDA(cudaEventCreate(&t->ev0));
+        for (auto& e : t->ev1) MB_CUDA(cudaEventCreate(&e));
+        MB_CUDA(cudaEventRecord(t->ev0, g.main));
+        for (auto& x : g.ctxs) MB_CUDA(cudaStreamWaitEvent(x.stream, t->ev0, 0));
 #endif
-        for (auto& x : g.ctxs) {
-            x.flag.ensure(4);
-            dev_memset(x.flag.p, 0, 4, x.stream);
-        }
-        for (size_t first = 0; first < n_proofs; first += g.chunk, ++ci) {
+        for (size_t first = 0; first < n_proofs; first += g.chunk) {
             uint32_t count = (uint32_t)std::min<size_t>(g.chunk, n_proofs - first);
-            ProveCtx& x = g.ctxs[ci % g.ctxs.size()];
-            prove_chunk(P, x, in, first, count, rows, staged);
+            ProveCtx& x = g.ctxs[g_next_ctx++ % g.ctxs.size()];
+            prove_chunk(P, x, in, first, count, rows, t->staged);
             // canonical-scalar check on what was just staged (abc and aux..s of the pool)
-            check_scalars_dev(x.abc.as<Fr>(), (size_t)count * 3 * rows, 0, 1, x.flag.as<uint32_t>(), x.stream);
+            check_scalars_dev(x.abc.as<Fr>(), (size_t)count * 3 * rows, 0, 1, t->flag.as<uint32_t>(), x.stream);
             check_scalars_dev(x.pool.as<Fr>() + P.idx_aux, P.idx_one - P.idx_aux, P.pool_stride, count,
-                              x.flag.as<uint32_t>(), x.stream);
-        }
-        uint32_t bad = 0;
-#ifndef MB200_EMU
-        for (size_t i = 0; i < g.ctxs.size(); ++i) MB_CUDA(cudaEventRecord(ev1[i], g.ctxs[i].stream));
-#endif
-        for (auto& x : g.ctxs) {
-            uint32_t b = 0;
-            copy_d2h(&b, x.flag.p, 4, x.stream);
-            stream_sync(x.stream);
-            bad |= b;
+                              t->flag.as<uint32_t>(), x.stream);
         }
 #ifndef MB200_EMU
-        g.last_batch_ms = 0;
-        for (auto& e : ev1) {
-            float ms = 0;
-            MB_CUDA(cudaEventElapsedTime(&ms, ev0, e));
-            if (ms > g.last_batch_ms) g.last_batch_ms = ms;
-            cudaEventDestroy(e);
-        }
-        cudaEventDestroy(ev0);
+        for (size_t i = 0; i < g.ctxs.size(); ++i) MB_CUDA(cudaEventRecord(t->ev1[i], g.ctxs[i].stream));
 #endif
-        if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
-        memcpy(proofs_out, staged, n_proofs * 192);
     } catch (...) {
-        for (auto& x : g.ctxs) {
 #ifndef MB200_EMU
-            cudaStreamSynchronize(x.stream);
+        for (auto& x : g.ctxs) cudaStreamSynchronize(x.stream);
 #endif
-        }
-        host_free_pinned(staged);
+        ticket_destroy(t);
         throw;
     }
-    host_free_pinned(staged);
+    uint64_t id = g_next_ticket++;
+    g_tickets[id] = t;
+    return id;
+}
+
+// Wait for a submitted batch, check its flag, hand the proofs to the caller.
+static void prove_wait(uint64_t id) {
+    auto it = g_tickets.find(id);
+    if (it == g_tickets.end()) fail(MB200_EINVAL, "unknown ticket%s (%ld)", "", (long)id);
+    Ticket* t = it->second;
+    g_tickets.erase(it);
+    uint32_t bad = 0;
+    try {
+#ifndef MB200_EMU
+        g.last_batch_ms = 0;
+        for (auto& e : t->ev1) {
+            MB_CUDA(cudaEventSynchronize(e));
+            float ms = 0;
+            MB_CUDA(cudaEventElapsedTime(&ms, t->ev0, e));
+            if (ms > g.last_batch_ms) g.last_batch_ms = ms;
+        }
+#endif
+        copy_d2h(&bad, t->flag.p, 4, g.main);
+        stream_sync(g.main);
+        if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
+        memcpy(t->out, t->staged, t->n_proofs * 192);
+    } catch (...) {
+        ticket_destroy(t);
+        throw;
+    }
+    ticket_destroy(t);
+}
+
+static int prove_impl(const Params& P, size_t n_proofs, size_t rows, const ProveInputs& in, uint8_t* proofs_out) {
+    require_init();
+    if (n_proofs == 0) return MB200_OK;
+    prove_wait(prove_submit(P, n_proofs, rows, in, proofs_out));
     return MB200_OK;
 }
 
@@ -344,6 +384,24 @@ int mb200_prove_batch_device(const mb200_params* p, size_t n_proofs, size_t rows
     ProveInputs in{(const uint8_t*)a_evals, (const uint8_t*)b_evals, (const uint8_t*)c_evals, (const uint8_t*)inputs,
                    (const uint8_t*)aux, (const uint8_t*)r, (const uint8_t*)s, true};
     return prove_impl(*p->p, n_proofs, rows, in, proofs_out);
+    MB_API_END
+}
+
+int mb200_prove_submit(const mb200_params* p, size_t n_proofs, size_t rows, const void* a_evals, const void* b_evals,
+                       const void* c_evals, const void* inputs, const void* aux, const void* r, const void* s,
+                       int on_device, uint8_t* proofs_out, uint64_t* ticket) {
+    MB_API_BEGIN
+    if (!p || !p->p || !ticket || n_proofs == 0) fail(MB200_EINVAL, "bad argument%s", "");
+    ProveInputs in{(const uint8_t*)a_evals, (const uint8_t*)b_evals, (const uint8_t*)c_evals, (const uint8_t*)inputs,
+                   (const uint8_t*)aux, (const uint8_t*)r, (const uint8_t*)s, on_device != 0};
+    *ticket = prove_submit(*p->p, n_proofs, rows, in, proofs_out);
+    MB_API_END
+}
+
+int mb200_prove_wait(uint64_t ticket) {
+    MB_API_BEGIN
+    require_init();
+    prove_wait(ticket);
     MB_API_END
 }
 

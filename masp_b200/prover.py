@@ -171,6 +171,20 @@ def prove_batch_raw(params, n_proofs, rows, a, b, c, inputs, aux, r, s, device=F
     return buf.raw if out is None else out
 
 
+def prove_submit(params, n_proofs, rows, a, b, c, inputs, aux, r, s, out, device=False):
+    """mb200_prove_submit: enqueue a batch, return a ticket.  `out` must be a
+    writable buffer of n_proofs * 192 bytes that outlives prove_wait."""
+    _ensure_init()
+    t = ctypes.c_uint64()
+    check(_lib.lib().mb200_prove_submit(params._h, n_proofs, rows, *[_ptr(x) for x in (a, b, c, inputs, aux, r, s)],
+                                        int(device), _ptr(out), ctypes.byref(t)))
+    return t.value
+
+
+def prove_wait(ticket):
+    check(_lib.lib().mb200_prove_wait(ticket))
+
+
 def create_proof(assignment, params, r, s):
     """bellman create_proof(circuit, params, r, s) after synthesis -> 192 bytes."""
     return create_proof_batch([assignment], params, [r], [s])[0]

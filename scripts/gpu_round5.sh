@@ -7,7 +7,7 @@ pv.init(0)
 print('fpmul/s %.3e' % pv.bench_fpmul())
 for m,n in ((0,'mul inline'),(1,'mul out-of-line'),(2,'xyzz dbl'),(3,'xyzz add')): print('%-16s %.0f ns/op' % (n, pv.bench_latency(m)))
 " 2>&1 | tee gpurun_out/latency.log
-echo "== msm sweep"; timeout 900 python scripts/msm_sweep.py --logs 16 18 20 22 --check 2>&1 | tee gpurun_out/msm_sweep_n1.log
+echo "== msm sweep"; timeout 900 python scripts/msm_sweep.py --sizes 16 18 20 22 --check 2>&1 | tee gpurun_out/msm_sweep_n1.log
 echo "== mixed"; timeout 600 python scripts/mixed_batch.py --mode mixed --tx 32 --check 1 2>&1 | tee gpurun_out/mixed_n1.log
 echo "== convert"; timeout 600 python scripts/mixed_batch.py --mode convert --per-gpu 128 --check 2 2>&1 | tee gpurun_out/convert_n1.log
 echo "== single proof latency"; timeout 300 python -c "

@@ -2,7 +2,7 @@
 """BASELINE config 3: standalone BLS12-381 G1 MSM sweep, bases range-split over
 the ranks, 192-byte projective partials all-gathered and added.
 
-  python scripts/msm_sweep.py --logs 16 18 20              # one GPU
+  python scripts/msm_sweep.py --sizes 16 18 20              # one GPU
   torchrun --nproc-per-node 8 scripts/msm_sweep.py ...      # bases split 8 ways
 
 Bases are PRNG scalars times the generator (known discrete logs), so every
@@ -29,7 +29,7 @@ import masp_b200.prover as pv  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--logs", type=int, nargs="+", default=[16, 18, 20, 22])
+    ap.add_argument("--sizes", type=int, nargs="+", default=[16, 18, 20, 22])
     ap.add_argument("--kinds", nargs="+", default=["U", "W"])
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--check", action="store_true")
@@ -44,7 +44,7 @@ def main():
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    for log_n in args.logs:
+    for log_n in args.sizes:
         n = 1 << log_n
         lo, hi = sharding.shard_range(n, rank, world)
         bases = pv.synth_points(syn.STREAM_MSM_BASE, lo, hi - lo, 1)   # this rank's range only

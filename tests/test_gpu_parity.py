@@ -219,3 +219,28 @@ def test_prove_all_zero_and_all_one_witness(gpu, oracle):
              "aux": aux_val * sh.n_aux, "r": zero, "s": zero}
         got = gpu.create_proof(assignment(gpu, w), P, w["r"], w["s"])
         assert got == oracle_proofs(oracle, kb, sh, dens, [w])[0]
+
+
+def test_streamed_batches_overlap_and_match(gpu, oracle):
+    """mb200_prove_submit / mb200_prove_wait: three batches in flight, waited out of order."""
+    import ctypes
+    sh = syn.tiny_shape()
+    kb = gpu.params_synthesize(sh)
+    dens = sh.densities()
+    P = gpu.Parameters.read(kb, dens)
+    batches, outs, tickets = [], [], []
+    for k in range(3):
+        ws = [syn.witness(sh, 10 * k + i, gpu.fr_mul) for i in range(4)]
+        cat = lambda key: b"".join(w[key] for w in ws)
+        bufs = [cat(key) for key in ("a", "b", "c", "inputs", "aux", "r", "s")]
+        out = ctypes.create_string_buffer(192 * len(ws))
+        tickets.append(gpu.prove_submit(P, len(ws), sh.rows, *bufs, ctypes.addressof(out)))
+        batches.append((ws, bufs))
+        outs.append(out)
+    for k in (1, 0, 2):
+        gpu.prove_wait(tickets[k])
+    for (ws, _), out in zip(batches, outs):
+        want = oracle_proofs(oracle, kb, sh, dens, ws)
+        assert [out.raw[192 * i:192 * (i + 1)] for i in range(len(ws))] == want
+    with pytest.raises(gpu.Mb200Error):
+        gpu.prove_wait(tickets[0])  # a ticket can be waited on once
