@@ -105,13 +105,19 @@ def test_spend_circuit_pins():
     assert (sum(dens[0]), sum(dens[1]), sum(dens[2])) == (syn.SPEND.a_dense, 1, syn.SPEND.b_dense)
 
 
-def real_output_instance():
-    """(cs, key bytes, densities, assignment byte strings, r, s) for the real Output circuit."""
+def real_instance(name):
+    """(cs, key bytes, densities, assignment byte strings) for a real MASP circuit
+    with a native witness and a trusted setup whose trapdoor is known."""
     from oracle.setup import generate_parameters_bytes
     ident, ag = mc.find_asset()
-    pk_d = mc.jj_mul(G_D, 999)
     cs = ConstraintSystem()
-    mc.output_circuit(cs, mc.bytes_to_bits_le(ident), ag, VALUE, RCV, G_D, pk_d, RCM, ESK)
+    if name == "output":
+        mc.output_circuit(cs, mc.bytes_to_bits_le(ident), ag, VALUE, RCV, G_D, mc.jj_mul(G_D, 999), RCM, ESK)
+    elif name == "convert":
+        mc.convert_circuit(cs, ag, VALUE, RCV, PATH, mc.convert_native_anchor(ag, PATH))
+    else:
+        nat = mc.spend_native(AK, NSK, G_D, ag, VALUE, RCV, RCM, AR, PATH)
+        mc.spend_circuit(cs, AK, NSK, G_D, ag, VALUE, RCV, RCM, AR, PATH, nat["anchor"])
     td = g.Trapdoor(0x1111111111222233334444, 0x5555AAAA, 0x7777BBBBCC, 0x99990000111, 0x1234567890ABCDEF)
     key, dens = generate_parameters_bytes(cs, td)
     a, b, c, d2 = cs.proving_assignment()
@@ -120,6 +126,10 @@ def real_output_instance():
     w = {"a": ib(a), "b": ib(b), "c": ib(c), "inputs": ib(cs.inputs), "aux": ib(cs.aux),
          "r": ib([0xDEADBEEFCAFEBABE1234]), "s": ib([0xFEEDFACE5678])}
     return cs, key, dens, w
+
+
+def real_output_instance():
+    return real_instance("output")
 
 
 def verify_with_pairing(key, proof_bytes, public_inputs):
@@ -144,14 +154,22 @@ def test_real_output_circuit_proof_verifies_cpu(oracle):
 
 
 @pytest.mark.gpu
-def test_real_output_circuit_proof_verifies_gpu(gpu, oracle):
-    """The CUDA path on the real MASP Output circuit: byte-identical to the CPU
-    oracle and accepted by the Groth16 verification equation."""
-    cs, key, dens, w = real_output_instance()
+@pytest.mark.parametrize("name", ["output", "convert", "spend"])
+def test_real_circuit_proofs_verify_gpu(gpu, oracle, name):
+    """The CUDA path on the real MASP circuits (real witnesses, real density
+    positions): byte-identical to the CPU oracle and accepted by the Groth16
+    verification equation, as the reference checks after proving
+    (masp_proofs/src/sapling/prover.rs:148, :266)."""
+    cs, key, dens, w = real_instance(name)
+    sh = syn.SHAPES[name]
+    assert len(key) == sh.params_file_bytes()
     P = gpu.Parameters.read(key, dens)
-    assert (P.n_inputs, P.n_aux, P.a_len, P.b_len) == (6, 30896, syn.OUTPUT.a_len, syn.OUTPUT.b_len)
+    assert (P.n_inputs, P.n_aux, P.a_len, P.b_len, P.m) == (sh.n_inputs, sh.n_aux, sh.a_len, sh.b_len, sh.m)
     asg = gpu.ProvingAssignment(w["a"], w["b"], w["c"], w["inputs"], w["aux"])
     proof = gpu.create_proof(asg, P, w["r"], w["s"])
     ref = oracle.Params(key, len(cs.aux), *dens)
     assert proof == ref.prove(asg.rows, w["a"], w["b"], w["c"], w["inputs"], w["aux"], w["r"], w["s"])
     assert verify_with_pairing(key, proof, cs.inputs[1:])
+    wrong = list(cs.inputs[1:])
+    wrong[-1] = (wrong[-1] + 1) % R
+    assert not verify_with_pairing(key, proof, wrong)
