@@ -37,6 +37,7 @@ extern "C" {
 #define MB200_ENOMEM (-4)
 #define MB200_ESTATE (-5)  /* mb200_init not called */
 #define MB200_ESCALAR (-6) /* a scalar is not canonical (>= r) */
+#define MB200_ESYNTH (-7)  /* witness generation failed (bellman SynthesisError: division by zero / unsatisfiable) */
 
 #define MB200_PROOF_BYTES 192 /* GROTH_PROOF_SIZE, masp_primitives/src/transaction/components.rs:14-15 */
 
@@ -102,6 +103,61 @@ int mb200_prove_submit(const mb200_params* p, size_t n_proofs, size_t rows, cons
                        const void* c_evals, const void* inputs, const void* aux, const void* r, const void* s,
                        int on_device, uint8_t* proofs_out, uint64_t* ticket);
 int mb200_prove_wait(uint64_t ticket);
+
+/* ---- circuits: the step in front of create_proof ----------
+ * The reference hands bellman a `Circuit` (masp_proofs/src/circuit/sapling.rs:
+ * Spend :139-417, Output :419-596; circuit/convert.rs: Convert :29-128) and
+ * bellman's ProvingAssignment runs its `synthesize` on the CPU for every proof,
+ * evaluating all constraints as it goes.  Here a circuit is recorded ONCE into
+ * an mb200_circuit (three CSR matrices, density bitmaps, structural hash);
+ * per proof the host only computes the witness (inputs + aux) and the GPU
+ * evaluates the rows (r1cs_eval kernel).
+ *
+ * A witness is a flat array of 32-byte little-endian fields; Jubjub points are
+ * affine (u, v), Jubjub scalars plain integers, value a u64 in the low 8 bytes,
+ * a Merkle path `depth` pairs (sibling scalar, is_right 0/1), leaf first:
+ *   Spend   (circuit::sapling::Spend):  ak.u ak.v nsk g_d.u g_d.v asset_generator.u .v
+ *                                       value rcv rcm ar anchor path...      (12 + 2 depth fields)
+ *   Output  (circuit::sapling::Output): asset_identifier[32 bytes] asset_generator.u .v
+ *                                       value rcv g_d.u g_d.v pk_d.u pk_d.v rcm esk    (11 fields)
+ *   Convert (circuit::convert::Convert): asset_generator.u .v value rcv anchor path... (5 + 2 depth)
+ */
+#define MB200_CIRCUIT_SPEND 0
+#define MB200_CIRCUIT_OUTPUT 1
+#define MB200_CIRCUIT_CONVERT 2
+typedef struct mb200_circuit mb200_circuit;
+/* merkle_depth: the reference uses 32 (masp_primitives/src/sapling.rs SAPLING_COMMITMENT_TREE_DEPTH);
+ * ignored for Output.  Host only: works without a device. */
+int mb200_circuit_new(int kind, uint32_t merkle_depth, mb200_circuit** out);
+void mb200_circuit_free(mb200_circuit* c);
+/* info[0..9] = n_inputs (incl. ONE), n_aux, n_constraints, nnz(A), nnz(B), nnz(C), witness bytes,
+ * ones in a_aux_density, b_input_density, b_aux_density */
+int mb200_circuit_info(const mb200_circuit* c, uint64_t info[10]);
+/* bellman TestConstraintSystem::hash of the recorded system, 64 hex digits + NUL: the value the
+ * reference pins at circuit/sapling.rs:730-741, 1024-1045 and circuit/convert.rs:218-224 */
+int mb200_circuit_hash(const mb200_circuit* c, char out_hex[65]);
+/* LSB-first bitmaps, (n_aux+7)/8, (n_inputs+7)/8, (n_aux+7)/8 bytes: what mb200_params_load takes */
+int mb200_circuit_densities(const mb200_circuit* c, uint8_t* a_aux, uint8_t* b_input, uint8_t* b_aux);
+/* CSR export of matrix 0/1/2 = A/B/C (any pointer may be NULL): rowptr[n_constraints+1], col[nnz]
+ * (input index, or 0x80000000 | aux index), coef[nnz x 32] canonical little-endian */
+int mb200_circuit_matrix(const mb200_circuit* c, int which, uint32_t* rowptr, uint32_t* col, uint8_t* coef);
+/* Circuit::synthesize, witness part only: n witnesses -> n x n_inputs and n x n_aux scalars.
+ * n_threads <= 0: all host threads.  MB200_ESCALAR: a field is out of range; MB200_ESYNTH: the
+ * reference's synthesis would have returned an error for this witness. */
+int mb200_circuit_synthesize(const mb200_circuit* c, size_t n, const uint8_t* witnesses, uint8_t* inputs_out,
+                             uint8_t* aux_out, int n_threads);
+/* The per-row evaluations a = A z, b = B z, c = C z of n witnesses, computed on the device:
+ * n x (n_constraints + n_inputs) scalars each, the trailing n_inputs rows being bellman's
+ * input rows (a = input_i, b = c = 0).  What ProvingAssignment holds after synthesize. */
+int mb200_circuit_rows(const mb200_circuit* c, size_t n, const uint8_t* inputs, const uint8_t* aux, uint8_t* a_out,
+                       uint8_t* b_out, uint8_t* c_out);
+/* Attach the circuit's matrices to a loaded key (uploads them once); the key's n_inputs / n_aux /
+ * query lengths must match the circuit's counts and densities. */
+int mb200_params_bind_circuit(mb200_params* p, const mb200_circuit* c);
+/* create_proof for a batch given only the witnesses; needs a bound circuit.  inputs / aux as
+ * produced by mb200_circuit_synthesize (host memory). */
+int mb200_prove_batch_witness(const mb200_params* p, size_t n_proofs, const uint8_t* inputs, const uint8_t* aux,
+                              const uint8_t* r, const uint8_t* s, uint8_t* proofs_out);
 
 /* multiexp over arbitrary bases (ec-gpu-gen `multiexp`, full density);
  * result uncompressed.  No table is precomputed on this path. */

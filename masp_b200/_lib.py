@@ -17,6 +17,8 @@ SYMBOLS = [
     "mb200_msm_g1_partial", "mb200_g1_sum_partials", "mb200_ntt", "mb200_h_coeffs", "mb200_fr_mul",
     "mb200_fr_mul_device", "mb200_set_option", "mb200_get_counter", "mb200_selftest", "mb200_bench_fpmul", "mb200_bench_latency",
     "mb200_strerror", "mb200_last_error",
+    "mb200_circuit_new", "mb200_circuit_free", "mb200_circuit_info", "mb200_circuit_hash", "mb200_circuit_densities",
+    "mb200_circuit_matrix", "mb200_circuit_synthesize", "mb200_circuit_rows", "mb200_params_bind_circuit", "mb200_prove_batch_witness",
 ]
 
 
@@ -64,6 +66,17 @@ def bind(path):
     L.mb200_selftest.argtypes = []
     L.mb200_bench_fpmul.argtypes = [c.POINTER(c.c_double)]
     L.mb200_bench_latency.argtypes = [c.c_int, c.POINTER(c.c_double)]
+    L.mb200_circuit_new.argtypes = [c.c_int, u32, c.POINTER(vp)]
+    L.mb200_circuit_free.argtypes = [vp]
+    L.mb200_circuit_free.restype = None
+    L.mb200_circuit_info.argtypes = [vp, c.POINTER(u64)]
+    L.mb200_circuit_hash.argtypes = [vp, u8p]
+    L.mb200_circuit_densities.argtypes = [vp, u8p, u8p, u8p]
+    L.mb200_circuit_matrix.argtypes = [vp, c.c_int, vp, vp, vp]
+    L.mb200_circuit_synthesize.argtypes = [vp, sz, u8p, u8p, u8p, c.c_int]
+    L.mb200_circuit_rows.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.mb200_params_bind_circuit.argtypes = [vp, vp]
+    L.mb200_prove_batch_witness.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.mb200_strerror.argtypes = [c.c_int]
     L.mb200_strerror.restype = u8p
     L.mb200_last_error.argtypes = []

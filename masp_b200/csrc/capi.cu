@@ -2,9 +2,11 @@
 // C++ above hand-written sm_100a kernels; no CPU compute path exists here:
 // every entry point needs mb200_init to have found a CUDA device.
 #include <algorithm>
+#include <array>
 #include <map>
 #include <mutex>
 
+#include "host/circuit_obj.hpp"
 #include "prover.cuh"
 #include "synth.cuh"
 #include "misc.cuh"
@@ -154,8 +156,13 @@ static void ticket_destroy(Ticket* t) {
 // Enqueue a whole batch on the chunk contexts; no host synchronisation.
 static uint64_t prove_submit(const Params& P, size_t n_proofs, size_t rows, const ProveInputs& in, uint8_t* proofs_out) {
     require_init();
-    if (!in.a || !in.b || !in.c || !in.inputs || !in.aux || !in.r || !in.s || !proofs_out)
+    if (!in.inputs || !in.aux || !in.r || !in.s || !proofs_out) fail(MB200_EINVAL, "null buffer%s", "");
+    if (!in.a && !in.b && !in.c) {  // witness-only: rows come from the bound circuit
+        if (!P.r1cs.bound) fail(MB200_EINVAL, "no circuit bound to these parameters%s", "");
+        if (rows != (size_t)P.r1cs.ncons + P.n_inputs) fail(MB200_EINVAL, "rows do not match the bound circuit%s", "");
+    } else if (!in.a || !in.b || !in.c) {
         fail(MB200_EINVAL, "null buffer%s", "");
+    }
     size_t m = 1;
     while (m < rows) m <<= 1;
     if (rows == 0 || m != P.m)
@@ -225,6 +232,49 @@ static void prove_wait(uint64_t id) {
         throw;
     }
     ticket_destroy(t);
+}
+
+// CSR matrices of a recorded circuit -> device, columns rewritten to scalar-pool
+// indices, coefficients interned into a dictionary (Montgomery form; 0 -> +1, 1 -> -1).
+static void r1cs_upload(R1csDev& R, const mb200_circuit& c, size_t idx_aux, size_t idx_inputs) {
+    std::map<std::array<uint64_t, 4>, uint32_t> dict;
+    std::vector<mbh::Fr> dict_vals;
+    auto intern = [&](const mbh::Fr& f) {
+        std::array<uint64_t, 4> k = {f.v[0], f.v[1], f.v[2], f.v[3]};
+        auto it = dict.find(k);
+        if (it != dict.end()) return it->second;
+        uint32_t id = (uint32_t)dict_vals.size();
+        dict[k] = id;
+        dict_vals.push_back(f);
+        return id;
+    };
+    intern(mbh::Fr::one());
+    intern(-mbh::Fr::one());
+    const mbh::Matrix* ms[3] = {&c.A, &c.B, &c.C};
+    for (int k = 0; k < 3; ++k) {
+        const mbh::Matrix& M = *ms[k];
+        std::vector<uint32_t> col(M.col.size()), cidx(M.col.size());
+        for (size_t e = 0; e < M.col.size(); ++e) {
+            uint32_t id = M.col[e];
+            col[e] = (id & mbh::Var::AUX) ? (uint32_t)idx_aux + (id & ~mbh::Var::AUX) : (uint32_t)idx_inputs + id;
+            cidx[e] = intern(M.coef[e]);
+        }
+        R.rowptr[k].alloc(M.rowptr.size() * 4);
+        R.col[k].alloc(col.size() * 4);
+        R.cidx[k].alloc(cidx.size() * 4);
+        copy_h2d(R.rowptr[k].p, M.rowptr.data(), M.rowptr.size() * 4, g.main);
+        copy_h2d(R.col[k].p, col.data(), col.size() * 4, g.main);
+        copy_h2d(R.cidx[k].p, cidx.data(), cidx.size() * 4, g.main);
+        stream_sync(g.main);  // the staging vectors die at the end of this iteration
+    }
+    // mbh::Fr (4 x u64 Montgomery, R = 2^256) has the same memory image as the device Fr (8 x u32)
+    R.dict.alloc(dict_vals.size() * 32);
+    copy_h2d(R.dict.p, dict_vals.data(), dict_vals.size() * 32, g.main);
+    stream_sync(g.main);
+    R.ncons = c.n_constraints;
+    R.n_inputs = c.n_inputs;
+    R.n_aux = c.n_aux;
+    R.bound = true;
 }
 
 static int prove_impl(const Params& P, size_t n_proofs, size_t rows, const ProveInputs& in, uint8_t* proofs_out) {
@@ -395,6 +445,73 @@ int mb200_prove_submit(const mb200_params* p, size_t n_proofs, size_t rows, cons
     ProveInputs in{(const uint8_t*)a_evals, (const uint8_t*)b_evals, (const uint8_t*)c_evals, (const uint8_t*)inputs,
                    (const uint8_t*)aux, (const uint8_t*)r, (const uint8_t*)s, on_device != 0};
     *ticket = prove_submit(*p->p, n_proofs, rows, in, proofs_out);
+    MB_API_END
+}
+
+int mb200_params_bind_circuit(mb200_params* p, const mb200_circuit* c) {
+    MB_API_BEGIN
+    require_init();
+    if (!p || !p->p || !c) fail(MB200_EINVAL, "null argument%s", "");
+    Params& P = *p->p;
+    if (P.n_inputs != c->n_inputs || P.n_aux != c->n_aux)
+        fail(MB200_EINVAL, "circuit and key disagree on the variable counts%s", "");
+    if (P.a_len != c->n_inputs + c->a_aux_ones || P.b_len != c->b_input_ones + c->b_aux_ones)
+        fail(MB200_EINVAL, "circuit densities do not match the key's query lengths%s", "");
+    size_t m = 1;
+    while (m < (size_t)c->n_constraints + c->n_inputs) m <<= 1;
+    if (m != P.m) fail(MB200_EINVAL, "circuit size does not match the key's domain%s", "");
+    r1cs_upload(P.r1cs, *c, P.idx_aux, P.idx_inputs);
+    MB_API_END
+}
+
+int mb200_circuit_rows(const mb200_circuit* c, size_t n, const uint8_t* inputs, const uint8_t* aux, uint8_t* a_out,
+                       uint8_t* b_out, uint8_t* c_out) {
+    MB_API_BEGIN
+    require_init();
+    if (!c || (n && (!inputs || !aux || !a_out || !b_out || !c_out))) fail(MB200_EINVAL, "null argument%s", "");
+    if (n == 0) return MB200_OK;
+    R1csDev R;
+    r1cs_upload(R, *c, 0, c->n_aux);
+    const size_t stride = (size_t)c->n_aux + c->n_inputs, rows = (size_t)c->n_constraints + c->n_inputs;
+    DevBuf pool(n * stride * 32), abc(n * 3 * rows * 32), flag(4);
+    dev_memset(flag.p, 0, 4, g.main);
+    uint8_t* pl = pool.as<uint8_t>();
+    copy_rows(pl, stride * 32, aux, (size_t)c->n_aux * 32, (size_t)c->n_aux * 32, n, false, g.main);
+    copy_rows(pl + (size_t)c->n_aux * 32, stride * 32, inputs, (size_t)c->n_inputs * 32, (size_t)c->n_inputs * 32, n, false,
+              g.main);
+    check_scalars_dev(pool.as<Fr>(), n * stride, 0, 1, flag.as<uint32_t>(), g.main);
+    R1csArgs ra;
+    ra.nthreads = n * rows;
+    for (int k = 0; k < 3; ++k) {
+        ra.rowptr[k] = R.rowptr[k].as<uint32_t>();
+        ra.col[k] = R.col[k].as<uint32_t>();
+        ra.cidx[k] = R.cidx[k].as<uint32_t>();
+    }
+    ra.dict = R.dict.as<Fr>();
+    ra.ncons = R.ncons;
+    ra.rows = (uint32_t)rows;
+    ra.pool = pool.as<Fr>();
+    ra.pool_stride = stride;
+    ra.idx_inputs = c->n_aux;
+    ra.abc = abc.as<Fr>();
+    launch_r1cs_eval(ra, g.main);
+    uint32_t bad = 0;
+    copy_d2h(&bad, flag.p, 4, g.main);
+    uint8_t* outs[3] = {a_out, b_out, c_out};
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k)
+            copy_d2h(outs[k] + i * rows * 32, abc.as<uint8_t>() + (i * 3 + k) * rows * 32, rows * 32, g.main);
+    stream_sync(g.main);
+    if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
+    MB_API_END
+}
+
+int mb200_prove_batch_witness(const mb200_params* p, size_t n_proofs, const uint8_t* inputs, const uint8_t* aux,
+                              const uint8_t* r, const uint8_t* s, uint8_t* proofs_out) {
+    MB_API_BEGIN
+    if (!p || !p->p) fail(MB200_EINVAL, "null parameters%s", "");
+    ProveInputs in{nullptr, nullptr, nullptr, inputs, aux, r, s, false};
+    return prove_impl(*p->p, n_proofs, (size_t)p->p->r1cs.ncons + p->p->n_inputs, in, proofs_out);
     MB_API_END
 }
 

@@ -20,6 +20,7 @@
 
 #include "msm.cuh"
 #include "ntt.cuh"
+#include "r1cs.cuh"
 
 namespace mb {
 
@@ -184,6 +185,7 @@ struct Params {
     MsmClass k_hl, k_a, k_b1, k_b2;
     NttDomain dom;
     std::vector<uint8_t> vk_bytes;  // the VerifyingKey prefix, verbatim
+    R1csDev r1cs;                   // the circuit's matrices, when one is bound (mb200_params_bind_circuit)
     size_t table_bytes = 0;
 };
 
@@ -404,9 +406,11 @@ inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, siz
 
     const size_t rb = rows * 32;
     uint8_t* abc = x.abc.as<uint8_t>();
-    copy_rows(abc, 3 * rb, in.a + first * rb, rb, rb, count, in.on_device, s);
-    copy_rows(abc + rb, 3 * rb, in.b + first * rb, rb, rb, count, in.on_device, s);
-    copy_rows(abc + 2 * rb, 3 * rb, in.c + first * rb, rb, rb, count, in.on_device, s);
+    if (in.a) {
+        copy_rows(abc, 3 * rb, in.a + first * rb, rb, rb, count, in.on_device, s);
+        copy_rows(abc + rb, 3 * rb, in.b + first * rb, rb, rb, count, in.on_device, s);
+        copy_rows(abc + 2 * rb, 3 * rb, in.c + first * rb, rb, rb, count, in.on_device, s);
+    }
     uint8_t* pool = x.pool.as<uint8_t>();
     const size_t pitch = P.pool_stride * 32;
     copy_rows(pool + P.idx_aux * 32, pitch, in.aux + first * P.n_aux * 32, (size_t)P.n_aux * 32, (size_t)P.n_aux * 32,
@@ -417,6 +421,25 @@ inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, siz
     copy_rows(pool + P.idx_s * 32, pitch, in.s + first * 32, 32, 32, count, in.on_device, s);
     FillOneArgs fo{count, x.pool.as<uint32_t>(), P.pool_stride, P.idx_one};
     launch_pool_fill_one(fo, s);
+    if (!in.a) {
+        // witness-only call: the row evaluations are a sparse product over the staged witness
+        const R1csDev& R = P.r1cs;
+        R1csArgs ra;
+        ra.nthreads = (size_t)count * rows;
+        for (int k = 0; k < 3; ++k) {
+            ra.rowptr[k] = R.rowptr[k].as<uint32_t>();
+            ra.col[k] = R.col[k].as<uint32_t>();
+            ra.cidx[k] = R.cidx[k].as<uint32_t>();
+        }
+        ra.dict = R.dict.as<Fr>();
+        ra.ncons = R.ncons;
+        ra.rows = (uint32_t)rows;
+        ra.pool = x.pool.as<Fr>();
+        ra.pool_stride = P.pool_stride;
+        ra.idx_inputs = P.idx_inputs;
+        ra.abc = x.abc.as<Fr>();
+        launch_r1cs_eval(ra, s);
+    }
 
     const uint32_t* pl = x.pool.as<uint32_t>();
     // fork: the A / B1 / B2 queries read aux, inputs, r, s only, so they run on

@@ -110,6 +110,14 @@ class Parameters:
         check(_lib.lib().mb200_params_info(h, info))
         return cls(h, [int(x) for x in info])
 
+    def bind_circuit(self, circuit):
+        """Attach a recorded circuit (masp_b200.circuits.Circuit): its matrices go to
+        the device once, after which create_proof_batch_from_witness needs only
+        the witnesses.  The key and the circuit must agree (counts, densities)."""
+        check(_lib.lib().mb200_params_bind_circuit(self._h, circuit._h))
+        self.circuit = circuit
+        return self
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
@@ -183,6 +191,25 @@ def prove_submit(params, n_proofs, rows, a, b, c, inputs, aux, r, s, out, device
 
 def prove_wait(ticket):
     check(_lib.lib().mb200_prove_wait(ticket))
+
+
+def create_proof_batch_from_witness(params, inputs, aux, r_s, s_s):
+    """create_proof_batch for a key with a bound circuit, from witnesses alone
+    (`inputs`, `aux` as Circuit.synthesize returns them): the row evaluations
+    bellman computes during synthesis are done on the device."""
+    _ensure_init()
+    n = len(r_s)
+    if n == 0:
+        return []
+    if len(s_s) != n or len(inputs) != 32 * n * params.n_inputs or len(aux) != 32 * n * params.n_aux:
+        raise ValueError("witness shape does not match the parameters")
+    to32 = lambda v: v if isinstance(v, (bytes, bytearray)) else int(v).to_bytes(32, "little")
+    out = ctypes.create_string_buffer(192 * n)
+    check(_lib.lib().mb200_prove_batch_witness(params._h, n, _ptr(inputs), _ptr(aux),
+                                               _ptr(b"".join(to32(v) for v in r_s)),
+                                               _ptr(b"".join(to32(v) for v in s_s)),
+                                               ctypes.cast(out, ctypes.c_void_p)))
+    return [out.raw[192 * i:192 * (i + 1)] for i in range(n)]
 
 
 def create_proof(assignment, params, r, s):

@@ -48,4 +48,11 @@ def load_emu():
     mod._lib = _EmuLib
     mod.check = _EmuLib.check
     mod.init()
+    # the circuit layer bound to the same build, so handles never cross libraries
+    cspec = importlib.util.find_spec("masp_b200.circuits")
+    cmod = importlib.util.module_from_spec(cspec)
+    cspec.loader.exec_module(cmod)
+    cmod._lib = _EmuLib
+    cmod.check = _EmuLib.check
+    mod.circuits = cmod
     return mod
