@@ -29,7 +29,9 @@ def _units():
 
 
 def _headers():
+    host = os.path.join(CSRC, "host")
     return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + \
+           [os.path.join(host, f) for f in os.listdir(host) if f.endswith(".hpp")] + \
            [os.path.join(ROOT, "include", "masp_b200.h")]
 
 
