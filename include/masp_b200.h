@@ -37,6 +37,7 @@ extern "C" {
 #define MB200_ENOMEM (-4)
 #define MB200_ESTATE (-5)  /* mb200_init not called */
 #define MB200_ESCALAR (-6) /* a scalar is not canonical (>= r) */
+#define MB200_EVERIFY (-8) /* a proof failed the self-check (the reference returns Err(()) at sapling/prover.rs:148, :266) */
 #define MB200_ESYNTH (-7)  /* witness generation failed (bellman SynthesisError: division by zero / unsatisfiable) */
 
 #define MB200_PROOF_BYTES 192 /* GROTH_PROOF_SIZE, masp_primitives/src/transaction/components.rs:14-15 */
@@ -146,6 +147,10 @@ int mb200_circuit_matrix(const mb200_circuit* c, int which, uint32_t* rowptr, ui
  * reference's synthesis would have returned an error for this witness. */
 int mb200_circuit_synthesize(const mb200_circuit* c, size_t n, const uint8_t* witnesses, uint8_t* inputs_out,
                              uint8_t* aux_out, int n_threads);
+/* The Merkle root a Spend / Convert witness leads to (the `cur` the circuit compares with the
+ * anchor, circuit/sapling.rs:343-372, convert.rs:96-124); the witness's own anchor field is ignored.
+ * For callers that hold a path but not the tree (tests, benches). */
+int mb200_circuit_root(const mb200_circuit* c, const uint8_t* witness, uint8_t root_out[32]);
 /* The per-row evaluations a = A z, b = B z, c = C z of n witnesses, computed on the device:
  * n x (n_constraints + n_inputs) scalars each, the trailing n_inputs rows being bellman's
  * input rows (a = input_i, b = c = 0).  What ProvingAssignment holds after synthesize. */
@@ -158,6 +163,18 @@ int mb200_params_bind_circuit(mb200_params* p, const mb200_circuit* c);
  * produced by mb200_circuit_synthesize (host memory). */
 int mb200_prove_batch_witness(const mb200_params* p, size_t n_proofs, const uint8_t* inputs, const uint8_t* aux,
                               const uint8_t* r, const uint8_t* s, uint8_t* proofs_out);
+
+/* ---- verification: groth16::verify_proof as the reference calls it right
+ * after proving (masp_proofs/src/sapling/prover.rs:148, :266), on the device, one thread per
+ * proof.  Two forms:
+ *   - mb200_set_option("verify", 1): every prove call checks its own proofs with the key's
+ *     verifying key and the witnesses' public inputs before returning them; a failure makes the
+ *     call return MB200_EVERIFY (the reference's Err(())).
+ *   - mb200_verify_batch: n proofs given as uncompressed points A (96) | B (192) | C (96) and
+ *     n x n_inputs public-input scalars (inputs[0] = 1); ok_out[i] = 1 iff
+ *     e(A,B) = e(alpha,beta) e(sum x_i IC_i, gamma) e(C, delta). */
+int mb200_verify_batch(const mb200_params* p, size_t n, const uint8_t* proofs_uncompressed, const uint8_t* inputs,
+                       uint8_t* ok_out);
 
 /* multiexp over arbitrary bases (ec-gpu-gen `multiexp`, full density);
  * result uncompressed.  No table is precomputed on this path. */
@@ -181,7 +198,7 @@ int mb200_h_coeffs(const uint8_t* a_evals, const uint8_t* b_evals, const uint8_t
 int mb200_fr_mul(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 int mb200_fr_mul_device(const void* a, const void* b, size_t n, void* out);
 
-/* knobs: "chunk" proofs per in-flight chunk; "streams" in-flight chunks */
+/* knobs: "chunk" proofs per in-flight chunk; "streams" in-flight chunks; "verify" 0/1 self-check */
 int mb200_set_option(const char* name, long value);
 /* counters: "launches" (kernels launched so far), "acc_launches",
  * "acc_us" (device time of the bucket-accumulation kernels, microseconds;

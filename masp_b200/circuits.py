@@ -32,6 +32,15 @@ PINS = {
 
 Point = Tuple[int, int]
 
+# fixed generators, affine (u, v): masp_primitives/src/constants.rs:50-251
+PROOF_GENERATION_KEY_GENERATOR = (0x4CAAEACAAF28ED4B4BA1F065E719FD031E24F83267F15ABD5F3C723AA2531B66,
+                                  0x00930D67D6906365C654DFDD36004DE936B49C71A2AF0708FE6F96BEC575BFF8)
+SPENDING_KEY_GENERATOR = (0x5B389522A9E81532F831C2B19FEC602639F5B03380AF6020EC75293D81248452,
+                          0x0CBC5F9F1E52E0AB75DEFECFF1F49EF22012D031F624FD5214B62623A186B4B1)
+VALUE_COMMITMENT_RANDOMNESS_GENERATOR = (0x1C6DA0CE9A5E5FDBCFA86026B8D99BE991CC3E3835675450DD93D364CB8CEC7E,
+                                         0x555F11F9B720D50BBC900CD4B8AE1150F94C2DAA360302FE28E5FCE99CE692D0)
+JUBJUB_ORDER = 0x0E7DB4EA6533AFA906673B0101343B00A6682093CCC81082D0970E5ED6F72CB7
+
 
 def _f(x):
     return int(x).to_bytes(32, "little")
@@ -140,18 +149,30 @@ class Circuit:
         vals = [int.from_bytes(coef.raw[32 * i:32 * i + 32], "little") for i in range(nnz)]
         return list(rp), list(col)[:nnz], vals
 
-    def synthesize(self, instances, threads=0):
+    def synthesize(self, instances, threads=0, numpy=False):
         """Witness half of Circuit::synthesize for a list of instances (or packed
-        witness bytes): returns (inputs bytes, aux bytes), n x n_inputs / n x n_aux scalars."""
+        witness bytes): returns (inputs, aux), n x n_inputs / n x n_aux scalars, as
+        bytes -- or, with numpy=True, as uint8 arrays written in place (no copies:
+        what a caller feeding the prover in a loop wants)."""
+        import numpy as np
         ws = [w if isinstance(w, (bytes, bytearray)) else w.pack() for w in instances]
         n = len(ws)
         for w in ws:
             if len(w) != self.witness_bytes:
                 raise ValueError("witness has %d bytes, this circuit takes %d" % (len(w), self.witness_bytes))
-        inp = ctypes.create_string_buffer(max(1, n * self.n_inputs * 32))
-        aux = ctypes.create_string_buffer(max(1, n * self.n_aux * 32))
-        check(_lib.lib().mb200_circuit_synthesize(self._h, n, b"".join(ws), inp, aux, threads))
-        return inp.raw[:n * self.n_inputs * 32], aux.raw[:n * self.n_aux * 32]
+        inp = np.empty(max(1, n * self.n_inputs * 32), dtype=np.uint8)
+        aux = np.empty(max(1, n * self.n_aux * 32), dtype=np.uint8)
+        check(_lib.lib().mb200_circuit_synthesize(self._h, n, b"".join(ws), inp.ctypes.data_as(ctypes.c_char_p),
+                                                  aux.ctypes.data_as(ctypes.c_char_p), threads))
+        inp, aux = inp[:n * self.n_inputs * 32], aux[:n * self.n_aux * 32]
+        return (inp, aux) if numpy else (inp.tobytes(), aux.tobytes())
+
+    def root(self, instance):
+        """The Merkle root this Spend / Convert witness leads to (its anchor field is ignored)."""
+        w = instance if isinstance(instance, (bytes, bytearray)) else instance.pack()
+        out = ctypes.create_string_buffer(32)
+        check(_lib.lib().mb200_circuit_root(self._h, bytes(w), out))
+        return int.from_bytes(out.raw, "little")
 
     def rows_on_device(self, inputs, aux, n):
         """(a, b, c) row evaluations of n witnesses, computed by the r1cs_eval kernel:

@@ -29,6 +29,7 @@ struct State {
     cudaStream_t main = 0;
     std::vector<ProveCtx> ctxs;
     uint32_t chunk = 64;
+    bool verify = false;  // option "verify": run the Groth16 check on every proof before returning it
     std::map<unsigned, NttCache*> ntt;
     MsmScratch msm;
     std::mutex mu;
@@ -130,6 +131,7 @@ static void check_scalars_dev(const Fr* base, size_t per_row, size_t row_stride,
 // One submitted batch: everything needed to finish it later.
 struct Ticket {
     uint8_t* staged = nullptr;  // pinned: proofs land here
+    uint32_t* verdicts = nullptr;  // pinned: per-proof result of the self-check (option "verify")
     uint8_t* out = nullptr;     // caller's buffer
     size_t n_proofs = 0;
     DevBuf flag;                // set by the canonical-scalar checks of this batch
@@ -150,6 +152,7 @@ static void ticket_destroy(Ticket* t) {
         if (e) cudaEventDestroy(e);
 #endif
     host_free_pinned(t->staged);
+    host_free_pinned(t->verdicts);
     delete t;
 }
 
@@ -172,6 +175,7 @@ static uint64_t prove_submit(const Params& P, size_t n_proofs, size_t rows, cons
         t->n_proofs = n_proofs;
         t->out = proofs_out;
         t->staged = (uint8_t*)host_alloc_pinned(n_proofs * 192);
+        if (g.verify) t->verdicts = (uint32_t*)host_alloc_pinned(n_proofs * 4);
         t->flag.alloc(4);
         dev_memset(t->flag.p, 0, 4, g.main);
 #ifndef MB200_EMU
@@ -185,7 +189,7 @@ static uint64_t prove_submit(const Params& P, size_t n_proofs, size_t rows, cons
         for (size_t first = 0; first < n_proofs; first += g.chunk) {
             uint32_t count = (uint32_t)std::min<size_t>(g.chunk, n_proofs - first);
             ProveCtx& x = g.ctxs[g_next_ctx++ % g.ctxs.size()];
-            prove_chunk(P, x, in, first, count, rows, t->staged);
+            prove_chunk(P, x, in, first, count, rows, t->staged, t->verdicts);
             // canonical-scalar check on what was just staged (abc and aux..s of the pool)
             check_scalars_dev(x.abc.as<Fr>(), (size_t)count * 3 * rows, 0, 1, t->flag.as<uint32_t>(), x.stream);
             check_scalars_dev(x.pool.as<Fr>() + P.idx_aux, P.idx_one - P.idx_aux, P.pool_stride, count,
@@ -227,6 +231,10 @@ static void prove_wait(uint64_t id) {
         stream_sync(g.main);
         if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
         memcpy(t->out, t->staged, t->n_proofs * 192);
+        if (t->verdicts)
+            for (size_t i = 0; i < t->n_proofs; ++i)
+                if (!t->verdicts[i])
+                    fail(MB200_EVERIFY, "proof %s%ld does not satisfy the verification equation", "", (long)i);
     } catch (...) {
         ticket_destroy(t);
         throw;
@@ -506,6 +514,54 @@ int mb200_circuit_rows(const mb200_circuit* c, size_t n, const uint8_t* inputs, 
     MB_API_END
 }
 
+int mb200_verify_batch(const mb200_params* p, size_t n, const uint8_t* proofs_uncompressed, const uint8_t* inputs,
+                       uint8_t* ok_out) {
+    MB_API_BEGIN
+    require_init();
+    if (!p || !p->p || (n && (!proofs_uncompressed || !inputs || !ok_out))) fail(MB200_EINVAL, "null argument%s", "");
+    if (n == 0) return MB200_OK;
+    const Params& P = *p->p;
+    // A | B | C in zkcrypto uncompressed form -> three device arrays
+    std::vector<uint8_t> ha(n * 96), hb(n * 192), hc(n * 96);
+    for (size_t i = 0; i < n; ++i) {
+        memcpy(&ha[i * 96], proofs_uncompressed + i * 384, 96);
+        memcpy(&hb[i * 192], proofs_uncompressed + i * 384 + 96, 192);
+        memcpy(&hc[i * 96], proofs_uncompressed + i * 384 + 288, 96);
+    }
+    DevBuf ra(n * 96), rb(n * 192), rc(n * 96), pa(n * sizeof(G1Affine)), pb(n * sizeof(G2Affine)),
+        pc(n * sizeof(G1Affine)), bad(4), din(n * P.n_inputs * 32), ok(n * 4);
+    copy_h2d(ra.p, ha.data(), ha.size(), g.main);
+    copy_h2d(rb.p, hb.data(), hb.size(), g.main);
+    copy_h2d(rc.p, hc.data(), hc.size(), g.main);
+    copy_h2d(din.p, inputs, n * P.n_inputs * 32, g.main);
+    dev_memset(bad.p, 0, 4, g.main);
+    DecodeArgs d1{n, ra.as<uint8_t>(), pa.p, bad.as<uint32_t>()}, d2{n, rb.as<uint8_t>(), pb.p, bad.as<uint32_t>()},
+        d3{n, rc.as<uint8_t>(), pc.p, bad.as<uint32_t>()};
+    launch_decode_g1(d1, g.main);
+    launch_decode_g2(d2, g.main);
+    launch_decode_g1(d3, g.main);
+    check_scalars_dev(din.as<Fr>(), n * P.n_inputs, 0, 1, bad.as<uint32_t>(), g.main);
+    VerifyArgs va;
+    va.nthreads = n;
+    va.pa = pa.as<G1Affine>();
+    va.pb = pb.as<G2Affine>();
+    va.pc = pc.as<G1Affine>();
+    va.inputs = din.as<uint32_t>();
+    va.input_stride = P.n_inputs;
+    va.n_inputs = P.n_inputs;
+    va.vk = {P.vk_ic.as<G1Affine>(), P.vk_g2.as<G2Affine>() + 1, P.vk_g2.as<G2Affine>() + 2, P.vk_ab.as<Fp12>()};
+    va.ok = ok.as<uint32_t>();
+    launch_verify_proofs(va, g.main);
+    std::vector<uint32_t> hok(n);
+    uint32_t hbad = 0;
+    copy_d2h(hok.data(), ok.p, n * 4, g.main);
+    copy_d2h(&hbad, bad.p, 4, g.main);
+    stream_sync(g.main);
+    if (hbad) fail(MB200_EPARSE, "malformed point or non-canonical input%s", "");
+    for (size_t i = 0; i < n; ++i) ok_out[i] = hok[i] ? 1 : 0;
+    MB_API_END
+}
+
 int mb200_prove_batch_witness(const mb200_params* p, size_t n_proofs, const uint8_t* inputs, const uint8_t* aux,
                               const uint8_t* r, const uint8_t* s, uint8_t* proofs_out) {
     MB_API_BEGIN
@@ -697,6 +753,8 @@ int mb200_set_option(const char* name, long value) {
     } else if (!strcmp(name, "streams")) {
         if (value < 1 || value > 8) fail(MB200_EINVAL, "streams out of range%s (%ld)", "", value);
         set_ctx_count((size_t)value);
+    } else if (!strcmp(name, "verify")) {
+        g.verify = value != 0;
     } else if (!strcmp(name, "profile")) {
         g_msm_profile.enabled = value != 0;
         g_msm_profile.acc_ms = 0;
@@ -810,6 +868,8 @@ const char* mb200_strerror(int code) {
         case MB200_ENOMEM: return "out of memory";
         case MB200_ESTATE: return "mb200_init has not been called";
         case MB200_ESCALAR: return "scalar is not canonical";
+        case MB200_ESYNTH: return "witness generation failed";
+        case MB200_EVERIFY: return "proof does not verify";
         default: return "unknown error";
     }
 }

@@ -300,6 +300,19 @@ int mb200_circuit_matrix(const mb200_circuit* c, int which, uint32_t* rowptr, ui
     return MB200_OK;
 }
 
+int mb200_circuit_root(const mb200_circuit* c, const uint8_t* witness, uint8_t root_out[32]) {
+    if (!c || !witness || !root_out || c->kind == MB200_CIRCUIT_OUTPUT) return MB200_EINVAL;
+    try {
+        CS cs;
+        if (!run_circuit(cs, c->kind, c->depth, witness)) return MB200_ESCALAR;
+        if (cs.failed) return MB200_ESYNTH;
+        cs.root.to_bytes(root_out);
+    } catch (const std::bad_alloc&) {
+        return MB200_ENOMEM;
+    }
+    return MB200_OK;
+}
+
 int mb200_circuit_synthesize(const mb200_circuit* c, size_t n, const uint8_t* witnesses, uint8_t* inputs_out,
                              uint8_t* aux_out, int n_threads) {
     if (!c || (n && (!witnesses || !inputs_out || !aux_out))) return MB200_EINVAL;

@@ -507,6 +507,7 @@ inline Bits merkle_and_anchor(CS& cs, AllocatedNum cur, const std::vector<AuthNo
         merkle_personalization((int)i, pers);
         cur = pedersen_hash(cs, pers, preimage).u;
     }
+    cs.root = cur.value;
     AllocatedNum rt = AllocatedNum::alloc(cs, anchor);
     cs.enforce(LC(cur.var, K().one).sub(rt.var), value_num.lc, LC());
     rt.inputize(cs);

@@ -91,6 +91,7 @@ struct CS {
     std::vector<Fr> inputs, aux;
     size_t n_constraints = 0;
     bool failed = false;  // a witness closure hit a division by zero (bellman: SynthesisError)
+    Fr root = Fr::zero(); // the Merkle root the circuit computed (Spend, Convert), for callers that need the anchor
     Matrix A, B, C;       // recorded rows (shape pass only)
     CS() { inputs.push_back(Fr::one()); }
 

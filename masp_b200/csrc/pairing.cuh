@@ -1,0 +1,264 @@
+// Groth16 verification on the device: the check the reference runs on the CPU
+// right after proving (`verify_proof(verifying_key, &proof, &public_input)` at
+// masp_proofs/src/sapling/prover.rs:148 and :266; SURVEY.md §8 a-8 / NEXT-3),
+//
+//     e(A, B) = e(alpha, beta) * e(sum x_i IC_i, gamma) * e(C, delta),
+//
+// one thread per proof of a batch.  A batch check is a few hundred thousand
+// dependent field multiplications per thread, i.e. latency-bound: it occupies a
+// handful of warps and runs next to the bucket kernels of the following chunk.
+//
+// Tower: Fp2 = Fp[u]/(u^2 + 1), Fp6 = Fp2[v]/(v^3 - (1 + u)), Fp12 = Fp6[w]/(w^2 - v);
+// optimal-ate Miller loop over |x| = 0xd201000000010000 with the G2 point kept
+// in Jacobian coordinates (no inversions; every line is scaled by an Fp2 factor,
+// which the final exponentiation kills); final exponentiation = easy part by
+// conjugation, one inversion and the p^2-Frobenius, hard part as a plain power
+// (p^4 - p^2 + 1) / r.
+#pragma once
+#include "ec.cuh"
+
+namespace mb {
+
+struct Fp6 {
+    Fp2 c0, c1, c2;
+};
+struct Fp12 {
+    Fp6 c0, c1;
+};
+
+struct PairConst {
+    // xi^((p^2 - 1) k / 6) for k = 1..5, all in Fp (Montgomery form)
+    MB_HD static Fp w(int k) {
+        constexpr uint32_t t[5][12] = {
+            {0x798dba3au, 0xecfb361bu, 0x91865a2cu, 0xc100ddb8u, 0x232bda8eu, 0x0ec08ff1u, 0xf1ca4721u, 0xd5c13cc6u, 0xbf7b5c04u, 0x47222a47u, 0xe51c5f59u, 0x0110f184u},
+            {0x798a64e8u, 0x30f1361bu, 0x7ece5a2au, 0xf3b8ddabu, 0xc61577f7u, 0x16a8ca3au, 0x74fd029bu, 0xc26a2ff8u, 0x60701c6eu, 0x3636b766u, 0x241b6160u, 0x051ba4abu},
+            {0xfffcaaaeu, 0x43f5ffffu, 0xed47fffdu, 0x32b7fff2u, 0xa2e99d69u, 0x07e83a49u, 0x8332bb7au, 0xeca8f331u, 0xa0f4c069u, 0xef148d1eu, 0x3eff0206u, 0x040ab326u},
+            {0x8671f071u, 0xcd03c9e4u, 0x1fcda5d2u, 0x5dab2246u, 0xd3851b95u, 0x587042afu, 0x01bacb9eu, 0x8eb60ebeu, 0x83d050d2u, 0x03f97d6eu, 0x54638741u, 0x18f02065u},
+            {0x867545c3u, 0x890dc9e4u, 0x3285a5d5u, 0x2af32253u, 0x309b7e2cu, 0x50880866u, 0x7e881024u, 0xa20d1b8cu, 0xe2db9068u, 0x14e4f04fu, 0x1564853au, 0x14e56d3fu}};
+        Fp r;
+        for (int i = 0; i < 12; ++i) r.v[i] = t[k - 1][i];
+        return r;
+    }
+    // (p^4 - p^2 + 1) / r, 1268 bits, little-endian words
+    MB_HD static uint32_t hard(int i) {
+        constexpr uint32_t t[40] = {
+            0x38e3ba79u, 0xe516c3f4u, 0xe208ccf1u, 0xfa9912aau, 0x335d5b68u, 0x905ce937u, 0xb0dea236u, 0xc71a2629u,
+            0x996754c8u, 0x83774940u, 0xb6a1e799u, 0x21d160aeu, 0xed237db4u, 0x2ed0b283u, 0x6c6f1821u, 0x915c97f3u,
+            0xde783765u, 0x67f17fcbu, 0x9096d1b7u, 0x2378b903u, 0x1bdc51dcu, 0x7988f876u, 0x03fc77a1u, 0x20769950u,
+            0xa621315bu, 0x827eca0bu, 0x8d63cb9fu, 0xe5a72bceu, 0xc28b6f8au, 0xf68f7764u, 0xcf081517u, 0x2f230063u,
+            0x528d6a9au, 0x94506632u, 0xeb996ca3u, 0xd3cde88eu, 0x195c899eu, 0xc0bd38c3u, 0x3d807d01u, 0x000f686bu};
+        return t[i];
+    }
+    static constexpr int HARD_BITS = 1268;
+    static constexpr unsigned long long X = 0xd201000000010000ull;  // |x|; x itself is negative
+};
+
+// ---------------------------------------------------------------------------
+// tower arithmetic (out of line: this code is latency-bound, keep it small)
+// ---------------------------------------------------------------------------
+MB_HD Fp2 f2_mul_xi(const Fp2& a) { return {Fp::sub(a.c0, a.c1), Fp::add(a.c0, a.c1)}; }
+MB_HD Fp2 f2_scale(const Fp2& a, const Fp& k) { return {Fp::mul(a.c0, k), Fp::mul(a.c1, k)}; }
+MB_COLD Fp2 f2_mul(const Fp2& a, const Fp2& b) { return Fp2::mul(a, b); }
+MB_COLD Fp2 f2_sqr(const Fp2& a) { return Fp2::sqr(a); }
+
+MB_HD Fp6 f6_zero() { return {Fp2::zero(), Fp2::zero(), Fp2::zero()}; }
+MB_HD Fp6 f6_add(const Fp6& a, const Fp6& b) { return {Fp2::add(a.c0, b.c0), Fp2::add(a.c1, b.c1), Fp2::add(a.c2, b.c2)}; }
+MB_HD Fp6 f6_sub(const Fp6& a, const Fp6& b) { return {Fp2::sub(a.c0, b.c0), Fp2::sub(a.c1, b.c1), Fp2::sub(a.c2, b.c2)}; }
+MB_HD Fp6 f6_neg(const Fp6& a) { return {Fp2::neg(a.c0), Fp2::neg(a.c1), Fp2::neg(a.c2)}; }
+MB_HD Fp6 f6_mul_v(const Fp6& a) { return {f2_mul_xi(a.c2), a.c0, a.c1}; }
+MB_COLD Fp6 f6_mul(const Fp6& a, const Fp6& b) {
+    Fp2 t0 = f2_mul(a.c0, b.c0), t1 = f2_mul(a.c1, b.c1), t2 = f2_mul(a.c2, b.c2);
+    Fp6 r;
+    r.c0 = Fp2::add(t0, f2_mul_xi(Fp2::add(f2_mul(a.c1, b.c2), f2_mul(a.c2, b.c1))));
+    r.c1 = Fp2::add(Fp2::add(f2_mul(a.c0, b.c1), f2_mul(a.c1, b.c0)), f2_mul_xi(t2));
+    r.c2 = Fp2::add(Fp2::add(f2_mul(a.c0, b.c2), f2_mul(a.c2, b.c0)), t1);
+    return r;
+}
+MB_COLD Fp6 f6_inv(const Fp6& a) {
+    Fp2 c0 = Fp2::sub(f2_sqr(a.c0), f2_mul_xi(f2_mul(a.c1, a.c2)));
+    Fp2 c1 = Fp2::sub(f2_mul_xi(f2_sqr(a.c2)), f2_mul(a.c0, a.c1));
+    Fp2 c2 = Fp2::sub(f2_sqr(a.c1), f2_mul(a.c0, a.c2));
+    Fp2 t = Fp2::add(f2_mul(a.c0, c0), f2_mul_xi(Fp2::add(f2_mul(a.c2, c1), f2_mul(a.c1, c2))));
+    Fp2 ti = Fp2::inv(t);
+    return {f2_mul(c0, ti), f2_mul(c1, ti), f2_mul(c2, ti)};
+}
+
+MB_HD Fp12 f12_one() { return {{Fp2::one(), Fp2::zero(), Fp2::zero()}, f6_zero()}; }
+MB_COLD Fp12 f12_mul(const Fp12& a, const Fp12& b) {
+    Fp6 t0 = f6_mul(a.c0, b.c0), t1 = f6_mul(a.c1, b.c1);
+    Fp12 r;
+    r.c1 = f6_sub(f6_sub(f6_mul(f6_add(a.c0, a.c1), f6_add(b.c0, b.c1)), t0), t1);
+    r.c0 = f6_add(t0, f6_mul_v(t1));
+    return r;
+}
+MB_HD Fp12 f12_conj(const Fp12& a) { return {a.c0, f6_neg(a.c1)}; }
+MB_COLD Fp12 f12_inv(const Fp12& a) {
+    Fp6 t = f6_sub(f6_mul(a.c0, a.c0), f6_mul_v(f6_mul(a.c1, a.c1)));
+    Fp6 ti = f6_inv(t);
+    return {f6_mul(a.c0, ti), f6_neg(f6_mul(a.c1, ti))};
+}
+// a^(p^2): the Fp2 coefficients are fixed, the basis element v^i w^j picks up xi^((p^2-1)(2i+j)/6)
+MB_COLD Fp12 f12_frob2(const Fp12& a) {
+    Fp12 r;
+    r.c0.c0 = a.c0.c0;
+    r.c0.c1 = f2_scale(a.c0.c1, PairConst::w(2));
+    r.c0.c2 = f2_scale(a.c0.c2, PairConst::w(4));
+    r.c1.c0 = f2_scale(a.c1.c0, PairConst::w(1));
+    r.c1.c1 = f2_scale(a.c1.c1, PairConst::w(3));
+    r.c1.c2 = f2_scale(a.c1.c2, PairConst::w(5));
+    return r;
+}
+MB_HD bool f12_is_one(const Fp12& a) {
+    return a.c0.c0.eq(Fp2::one()) && a.c0.c1.is_zero() && a.c0.c2.is_zero() && a.c1.c0.is_zero() && a.c1.c1.is_zero() &&
+           a.c1.c2.is_zero();
+}
+
+// ---------------------------------------------------------------------------
+// Miller loop
+// ---------------------------------------------------------------------------
+struct G2Jac {
+    Fp2 x, y, z;
+};
+// line through the untwisted T, scaled by an Fp2 factor, evaluated at P = (xp, yp):
+//   c_w3 * yp * w^3  +  c_w2 * xp * w^2  +  c_1        (w^2 = v, w^3 = v w)
+MB_HD Fp12 line_value(const Fp2& c_1, const Fp2& c_w2, const Fp2& c_w3, const G1Affine& p) {
+    Fp12 l;
+    l.c0 = {c_1, f2_scale(c_w2, p.x), Fp2::zero()};
+    l.c1 = {Fp2::zero(), f2_scale(c_w3, p.y), Fp2::zero()};
+    return l;
+}
+// T <- 2 T; returns the tangent line at (the old) T
+MB_COLD Fp12 miller_double(G2Jac& t, const G1Affine& p) {
+    Fp2 A = f2_sqr(t.x), B = f2_sqr(t.y), C = f2_sqr(B), Z2 = f2_sqr(t.z);
+    Fp2 N = Fp2::add(Fp2::dbl(A), A);            // 3 X^2
+    Fp2 D = Fp2::dbl(f2_mul(t.y, t.z));          // 2 Y Z
+    // lambda = N / D; line * (D Z^2):  (D Z^2) yp w^3 - (N Z^2) xp w^2 + (N X - 2 Y^2)
+    Fp12 l = line_value(Fp2::sub(f2_mul(N, t.x), Fp2::dbl(B)), Fp2::neg(f2_mul(N, Z2)), f2_mul(D, Z2), p);
+    Fp2 S = Fp2::dbl(Fp2::dbl(f2_mul(t.x, B)));  // 4 X Y^2
+    Fp2 X3 = Fp2::sub(f2_sqr(N), Fp2::dbl(S));
+    Fp2 C8 = Fp2::dbl(Fp2::dbl(Fp2::dbl(C)));
+    t.y = Fp2::sub(f2_mul(N, Fp2::sub(S, X3)), C8);
+    t.x = X3;
+    t.z = D;
+    return l;
+}
+// T <- T + Q (Q affine); returns the chord through T and Q
+MB_COLD Fp12 miller_add(G2Jac& t, const G2Affine& q, const G1Affine& p) {
+    Fp2 Z2 = f2_sqr(t.z);
+    Fp2 Z3 = f2_mul(Z2, t.z);
+    Fp2 theta = Fp2::sub(t.y, f2_mul(q.y, Z3));
+    Fp2 mu = Fp2::sub(t.x, f2_mul(q.x, Z2));
+    Fp2 D = f2_mul(t.z, mu);
+    // lambda = theta / D; line * D:  D yp w^3 - theta xp w^2 + (theta xq - D yq)
+    Fp12 l = line_value(Fp2::sub(f2_mul(theta, q.x), f2_mul(D, q.y)), Fp2::neg(theta), D, p);
+    Fp2 mu2 = f2_sqr(mu);
+    Fp2 mu3 = f2_mul(mu2, mu);
+    Fp2 xm2 = f2_mul(t.x, mu2);
+    Fp2 X3 = Fp2::sub(Fp2::add(f2_sqr(theta), mu3), Fp2::dbl(xm2));
+    t.y = Fp2::sub(f2_mul(theta, Fp2::sub(xm2, X3)), f2_mul(t.y, mu3));
+    t.x = X3;
+    t.z = D;
+    return l;
+}
+// prod_i f_{|x|,Q_i}(P_i), conjugated (x < 0); pairs with an identity contribute 1
+MB_COLD Fp12 miller_multi(const G1Affine* ps, const G2Affine* qs, int n) {
+    G2Jac t[3];
+    bool live[3];
+    for (int i = 0; i < n; ++i) {
+        live[i] = !ps[i].is_inf() && !qs[i].is_inf();
+        t[i] = {qs[i].x, qs[i].y, Fp2::one()};
+    }
+    Fp12 f = f12_one();
+    MB_NOUNROLL
+    for (int bit = 62; bit >= 0; --bit) {
+        f = f12_mul(f, f);
+        MB_NOUNROLL
+        for (int i = 0; i < n; ++i)
+            if (live[i]) f = f12_mul(f, miller_double(t[i], ps[i]));
+        if ((PairConst::X >> bit) & 1) {
+            MB_NOUNROLL
+            for (int i = 0; i < n; ++i)
+                if (live[i]) f = f12_mul(f, miller_add(t[i], qs[i], ps[i]));
+        }
+    }
+    return f12_conj(f);
+}
+MB_COLD Fp12 final_exponentiation(const Fp12& f) {
+    Fp12 f1 = f12_mul(f12_conj(f), f12_inv(f));  // f^(p^6 - 1)
+    Fp12 f2 = f12_mul(f12_frob2(f1), f1);        // ^(p^2 + 1)
+    Fp12 r = f12_one();
+    MB_NOUNROLL
+    for (int i = PairConst::HARD_BITS - 1; i >= 0; --i) {
+        r = f12_mul(r, r);
+        if ((PairConst::hard(i >> 5) >> (i & 31)) & 1) r = f12_mul(r, f2);
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+// Verifying key on the device (from the vk prefix of the Parameters bytes)
+struct VkDev {
+    const G1Affine* ic;      // n_inputs points
+    const G2Affine* gamma;   // gamma_g2
+    const G2Affine* delta;   // delta_g2
+    const Fp12* alpha_beta;  // Miller value of (-alpha_g1, beta_g2), computed once per key
+};
+
+struct PairPrepArgs {
+    size_t nthreads;  // 1
+    const G1Affine* alpha;
+    const G2Affine* beta;
+    Fp12* out;
+};
+MB_HD void pair_prep_body(const PairPrepArgs& a, size_t) {
+    G1Affine p = *a.alpha;
+    p.y = Fp::neg(p.y);
+    G2Affine q = *a.beta;
+    *a.out = miller_multi(&p, &q, 1);
+}
+
+struct VerifyArgs {
+    size_t nthreads;  // proofs
+    const G1Affine* pa;  // proof.A
+    const G2Affine* pb;  // proof.B
+    const G1Affine* pc;  // proof.C
+    const uint32_t* inputs;   // per proof: n_inputs scalars (plain, 8 words each), inputs[0] = 1
+    size_t input_stride;      // in scalars
+    uint32_t n_inputs;
+    VkDev vk;
+    uint32_t* ok;  // per proof: 1 = the equation holds
+};
+MB_HD void verify_body(const VerifyArgs& a, size_t tid) {
+    // acc = IC_0 + sum_{i >= 1} x_i IC_i
+    G1XYZZ acc = G1XYZZ::from_affine(a.vk.ic[0]);
+    const uint32_t* x = a.inputs + tid * a.input_stride * 8;
+    MB_NOUNROLL
+    for (uint32_t i = 1; i < a.n_inputs; ++i) {
+        G1XYZZ t = xyzz_mul(G1XYZZ::from_affine(a.vk.ic[i]), x + 8 * i);
+        xyzz_add_cold(acc, t);
+    }
+    G1Affine ps[3];
+    G2Affine qs[3];
+    ps[0] = a.pa[tid];
+    qs[0] = a.pb[tid];
+    ps[1] = xyzz_to_affine(acc);
+    ps[1].y = Fp::neg(ps[1].y);
+    qs[1] = *a.vk.gamma;
+    ps[2] = a.pc[tid];
+    ps[2].y = Fp::neg(ps[2].y);
+    qs[2] = *a.vk.delta;
+    Fp12 f = f12_mul(miller_multi(ps, qs, 3), *a.vk.alpha_beta);
+    a.ok[tid] = f12_is_one(final_exponentiation(f)) ? 1u : 0u;
+}
+
+#ifdef MB_DEFINE_PAIR
+MB_KERNEL_DEF(pair_prep, PairPrepArgs, pair_prep_body, 32)
+MB_KERNEL_DEF(verify_proofs, VerifyArgs, verify_body, 32)
+#else
+MB_KERNEL_DECL(pair_prep, PairPrepArgs)
+MB_KERNEL_DECL(verify_proofs, VerifyArgs)
+#endif
+
+}  // namespace mb

@@ -20,6 +20,7 @@
 
 #include "msm.cuh"
 #include "ntt.cuh"
+#include "pairing.cuh"
 #include "r1cs.cuh"
 
 namespace mb {
@@ -117,20 +118,29 @@ struct FinishArgs {
     const G1XYZZ* hl_res;
     const G1XYZZ* cmul;  // [proofs][2]
     uint8_t* proofs;     // 192 bytes each
+    G1Affine* aff_a;     // optional (self-check): the three points in affine form
+    G2Affine* aff_b;
+    G1Affine* aff_c;
 };
 MB_HD void finish_body(const FinishArgs& a, size_t tid) {
     size_t proof = tid / 3;
     uint32_t which = (uint32_t)(tid - proof * 3);
     uint8_t* out = a.proofs + 192 * proof;
     if (which == 0) {
-        g1_encode_compressed(xyzz_to_affine(a.a_res[proof]), out);
+        G1Affine p = xyzz_to_affine(a.a_res[proof]);
+        if (a.aff_a) a.aff_a[proof] = p;
+        g1_encode_compressed(p, out);
     } else if (which == 1) {
-        g2_encode_compressed(xyzz_to_affine(a.b2_res[proof]), out + 48);
+        G2Affine p = xyzz_to_affine(a.b2_res[proof]);
+        if (a.aff_b) a.aff_b[proof] = p;
+        g2_encode_compressed(p, out + 48);
     } else {
         G1XYZZ c = a.hl_res[proof];
         xyzz_add_cold(c, a.cmul[2 * proof]);
         xyzz_add_cold(c, a.cmul[2 * proof + 1]);
-        g1_encode_compressed(xyzz_to_affine(c), out + 144);
+        G1Affine p = xyzz_to_affine(c);
+        if (a.aff_c) a.aff_c[proof] = p;
+        g1_encode_compressed(p, out + 144);
     }
 }
 MB_K_G2(proof_finish, FinishArgs, finish_body, 32)
@@ -185,6 +195,7 @@ struct Params {
     MsmClass k_hl, k_a, k_b1, k_b2;
     NttDomain dom;
     std::vector<uint8_t> vk_bytes;  // the VerifyingKey prefix, verbatim
+    DevBuf vk_g1, vk_g2, vk_ic, vk_ab;  // alpha_g1 | beta, gamma, delta (G2) | IC | Miller(-alpha, beta): the self-check
     R1csDev r1cs;                   // the circuit's matrices, when one is bound (mb200_params_bind_circuit)
     size_t table_bytes = 0;
 };
@@ -328,10 +339,18 @@ inline Params* params_load(const uint8_t* buf, size_t len, const uint8_t* a_aux_
     dec2(o_b2, n_b2, b_b2.as<G2Affine>());
     dec2(672, 1, b_b2.as<G2Affine>() + n_b2);
     dec2(192, 1, b_b2.as<G2Affine>() + n_b2 + 1);
-    // the remaining vk points are only checked for well-formedness
-    DevBuf scratch((size_t)(n_ic + 1) * sizeof(G2Affine));
-    dec2(384, 1, scratch.as<G2Affine>());
-    dec1(o_ic, n_ic, scratch.as<G1Affine>());
+    // the verifying key, kept for the post-proof self-check (pairing.cuh)
+    P->vk_g1.alloc(sizeof(G1Affine));
+    P->vk_g2.alloc(3 * sizeof(G2Affine));
+    P->vk_ic.alloc((size_t)n_ic * sizeof(G1Affine));
+    P->vk_ab.alloc(sizeof(Fp12));
+    dec1(0, 1, P->vk_g1.as<G1Affine>());
+    dec2(192, 1, P->vk_g2.as<G2Affine>());
+    dec2(384, 1, P->vk_g2.as<G2Affine>() + 1);
+    dec2(672, 1, P->vk_g2.as<G2Affine>() + 2);
+    dec1(o_ic, n_ic, P->vk_ic.as<G1Affine>());
+    PairPrepArgs pp{1, P->vk_g1.as<G1Affine>(), P->vk_g2.as<G2Affine>(), P->vk_ab.as<Fp12>()};
+    launch_pair_prep(pp, s);
 
     // window sizes: full-width share guessed from the reference circuits
     // (SURVEY §8 scalar make-up: ~1/3 of L, ~1/5 of A and B are full width)
@@ -360,6 +379,7 @@ struct ProveCtx {  // one in-flight chunk: its streams and scratch
     cudaStream_t stream = 0;      // copies, NTT, H+L MSM, assembly
     cudaStream_t side[3] = {0, 0, 0};  // A, B1, B2 MSMs: they need only the staged witness, not the NTT
     DevBuf abc, w0, w1, w2, w3, pool, flag, res_hl, res_a, res_b1, res_b2, cmul, proofs;
+    DevBuf aff_a, aff_b, aff_c, ok;  // self-check: affine proof points, per-proof verdict
     MsmScratch msm, msm_side[3];
     bool have_stream = false;
 #ifndef MB200_EMU
@@ -386,8 +406,9 @@ inline void copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, 
 
 // Enqueue one chunk of proofs [first, first + count) on ctx.stream.  proofs_out:
 // host memory, 192 bytes per proof.  No host synchronisation.
+// verify_out: pinned host array of per-proof verdicts, or nullptr to skip the self-check.
 inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, size_t first, uint32_t count,
-                        size_t rows, uint8_t* proofs_out) {
+                        size_t rows, uint8_t* proofs_out, uint32_t* verify_out = nullptr) {
     cudaStream_t s = x.stream;
     const uint32_t m = P.m;
     size_t polys = (size_t)count * 3;
@@ -468,9 +489,33 @@ inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, siz
                 x.cmul.as<G1XYZZ>()};
     launch_proof_cmul(ca, s);
     FinishArgs fa{(size_t)count * 3, x.res_a.as<G1XYZZ>(), x.res_b2.as<G2XYZZ>(), x.res_hl.as<G1XYZZ>(),
-                  x.cmul.as<G1XYZZ>(), x.proofs.as<uint8_t>()};
+                  x.cmul.as<G1XYZZ>(), x.proofs.as<uint8_t>(), nullptr, nullptr, nullptr};
+    if (verify_out) {
+        x.aff_a.ensure(count * sizeof(G1Affine));
+        x.aff_b.ensure(count * sizeof(G2Affine));
+        x.aff_c.ensure(count * sizeof(G1Affine));
+        x.ok.ensure((size_t)count * 4);
+        fa.aff_a = x.aff_a.as<G1Affine>();
+        fa.aff_b = x.aff_b.as<G2Affine>();
+        fa.aff_c = x.aff_c.as<G1Affine>();
+    }
     launch_proof_finish(fa, s);
     copy_d2h(proofs_out + first * 192, x.proofs.p, (size_t)count * 192, s);
+    if (verify_out) {
+        // verify_proof(vk, proof, inputs) as at masp_proofs/src/sapling/prover.rs:148, :266
+        VerifyArgs va;
+        va.nthreads = count;
+        va.pa = fa.aff_a;
+        va.pb = fa.aff_b;
+        va.pc = fa.aff_c;
+        va.inputs = x.pool.as<uint32_t>() + P.idx_inputs * 8;
+        va.input_stride = P.pool_stride;
+        va.n_inputs = P.n_inputs;
+        va.vk = {P.vk_ic.as<G1Affine>(), P.vk_g2.as<G2Affine>() + 1, P.vk_g2.as<G2Affine>() + 2, P.vk_ab.as<Fp12>()};
+        va.ok = x.ok.as<uint32_t>();
+        launch_verify_proofs(va, s);
+        copy_d2h(verify_out + first, x.ok.p, (size_t)count * 4, s);
+    }
 }
 
 }  // namespace mb

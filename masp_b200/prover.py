@@ -71,6 +71,8 @@ def get_counter(name):
 
 def _ptr(x):
     """Host bytes-like or an integer device / pinned-host address -> c_void_p."""
+    if x is None:
+        return ctypes.c_void_p(None)
     if isinstance(x, int):
         return ctypes.c_void_p(x)
     if isinstance(x, (bytes, bytearray)):
@@ -189,6 +191,13 @@ def prove_submit(params, n_proofs, rows, a, b, c, inputs, aux, r, s, out, device
     return t.value
 
 
+def prove_submit_witness(params, n_proofs, inputs, aux, r, s, out):
+    """Streaming form of create_proof_batch_from_witness: enqueue, return a ticket
+    (mb200_prove_submit with no row evaluations: the bound circuit supplies them)."""
+    rows = params.circuit.rows
+    return prove_submit(params, n_proofs, rows, None, None, None, inputs, aux, r, s, out)
+
+
 def prove_wait(ticket):
     check(_lib.lib().mb200_prove_wait(ticket))
 
@@ -201,7 +210,8 @@ def create_proof_batch_from_witness(params, inputs, aux, r_s, s_s):
     n = len(r_s)
     if n == 0:
         return []
-    if len(s_s) != n or len(inputs) != 32 * n * params.n_inputs or len(aux) != 32 * n * params.n_aux:
+    nbytes = lambda x: x.nbytes if hasattr(x, "nbytes") else len(x)
+    if len(s_s) != n or nbytes(inputs) != 32 * n * params.n_inputs or nbytes(aux) != 32 * n * params.n_aux:
         raise ValueError("witness shape does not match the parameters")
     to32 = lambda v: v if isinstance(v, (bytes, bytearray)) else int(v).to_bytes(32, "little")
     out = ctypes.create_string_buffer(192 * n)
@@ -210,6 +220,25 @@ def create_proof_batch_from_witness(params, inputs, aux, r_s, s_s):
                                                _ptr(b"".join(to32(v) for v in s_s)),
                                                ctypes.cast(out, ctypes.c_void_p)))
     return [out.raw[192 * i:192 * (i + 1)] for i in range(n)]
+
+
+def verify_batch(params, proofs_uncompressed, public_inputs):
+    """groth16::verify_proof on the device for a batch (mb200_verify_batch).
+    proofs_uncompressed: list of 384-byte A | B | C encodings (zkcrypto
+    uncompressed); public_inputs: per proof the list of input scalars WITHOUT
+    the leading ONE, as verify_proof's `public_inputs` slice.  Returns a list of bools."""
+    _ensure_init()
+    n = len(proofs_uncompressed)
+    if n == 0:
+        return []
+    inp = b"".join((1).to_bytes(32, "little") + b"".join(int(x).to_bytes(32, "little") for x in xs)
+                   for xs in public_inputs)
+    if len(inp) != 32 * n * params.n_inputs:
+        raise ValueError("public input count does not match the verifying key")
+    ok = ctypes.create_string_buffer(n)
+    check(_lib.lib().mb200_verify_batch(params._h, n, _ptr(b"".join(proofs_uncompressed)), _ptr(inp),
+                                        ctypes.cast(ok, ctypes.c_void_p)))
+    return [b != 0 for b in ok.raw]
 
 
 def create_proof(assignment, params, r, s):
