@@ -265,7 +265,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-circuit-path", action="store_true")
     ap.add_argument("--circuit-batch", type=int, default=64, help="real-witness leg: proofs per round")
-    ap.add_argument("--circuit-rounds", type=int, default=6)
+    ap.add_argument("--circuit-rounds", type=int, default=12)
     args = ap.parse_args()
     shape = syn.SHAPES[args.circuit]
 

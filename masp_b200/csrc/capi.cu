@@ -52,18 +52,39 @@ static void set_ctx_count(size_t n) {
                 cudaStreamDestroy(c.side[i]);
                 cudaEventDestroy(c.ev_side[i]);
             }
+            for (int i = 0; i < 4; ++i) {
+                cudaStreamSynchronize(c.tail[i]);
+                cudaStreamDestroy(c.tail[i]);
+                cudaEventDestroy(c.ev_acc[i]);
+            }
+            cudaEventDestroy(c.ev_tail);
         }
 #endif
     g.ctxs.clear();
     g.ctxs.resize(n);
 #ifndef MB200_EMU
+    // Throughput kernels (copies, NTT, digit sort, bucket accumulation) run on low-priority
+    // streams; the latency-bound tails (bucket reduction, s*A and r*B1, encoding, self-check) on
+    // high-priority ones, so that their few blocks are placed as soon as any SM has room instead
+    // of queueing behind the thousands of pending accumulation blocks of the next chunk.
+    int pr_least = 0, pr_greatest = 0;
+    MB_CUDA(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+    // measured on B200 (profiles/r01_tail_streams_ab.jsonl): no gain over the single-stream tails,
+    // the accumulation blocks hold the register file either way -- kept as an opt-in experiment
+    const bool split = getenv("MB200_TAIL_STREAMS") != nullptr;
     for (auto& c : g.ctxs) {
-        MB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        MB_CUDA(cudaStreamCreateWithPriority(&c.stream, cudaStreamNonBlocking, pr_least));
         MB_CUDA(cudaEventCreateWithFlags(&c.ev_inputs, cudaEventDisableTiming));
         for (int i = 0; i < 3; ++i) {
-            MB_CUDA(cudaStreamCreateWithFlags(&c.side[i], cudaStreamNonBlocking));
+            MB_CUDA(cudaStreamCreateWithPriority(&c.side[i], cudaStreamNonBlocking, pr_least));
             MB_CUDA(cudaEventCreateWithFlags(&c.ev_side[i], cudaEventDisableTiming));
         }
+        for (int i = 0; i < 4; ++i) {
+            MB_CUDA(cudaStreamCreateWithPriority(&c.tail[i], cudaStreamNonBlocking, pr_greatest));
+            MB_CUDA(cudaEventCreateWithFlags(&c.ev_acc[i], cudaEventDisableTiming));
+        }
+        MB_CUDA(cudaEventCreateWithFlags(&c.ev_tail, cudaEventDisableTiming));
+        c.split_tail = split;
         c.have_stream = true;
     }
 #endif

@@ -402,6 +402,11 @@ struct MsmProfile {  // optional CUDA-event timing of the accumulate kernel
 extern MsmProfile g_msm_profile;
 
 static const uint32_t RED_T = 16, RED_LOG_T = 4, SCAN_CHUNK = 512;
+inline uint32_t red_log_t(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    uint32_t x = (v && *v) ? (uint32_t)strtoul(v, nullptr, 10) : dflt;
+    return x < 1 ? 1 : (x > 8 ? 8 : x);
+}
 
 template <class F>
 inline void launch_acc(const AccArgs<F>& a, cudaStream_t s);
@@ -428,10 +433,27 @@ inline void launch_horner<Fp>(const HornerArgs<Fp>& a, cudaStream_t s) { launch_
 template <>
 inline void launch_horner<Fp2>(const HornerArgs<Fp2>& a, cudaStream_t s) { launch_msm_horner_g2(a, s); }
 
-// Runs one class over n_inst instances.  out: n_inst XYZZ results (device).
+// Optional second stream for the latency-bound part of an MSM (bucket combine + reduction):
+// `ev` is recorded on the main stream after the accumulation and awaited by `stream`.
+struct MsmTail {
+    cudaStream_t stream = 0;
+#ifndef MB200_EMU
+    cudaEvent_t ev = nullptr;
+#endif
+    bool on() const {
+#ifndef MB200_EMU
+        return ev != nullptr;
+#else
+        return false;
+#endif
+    }
+};
+
+// Runs one class over n_inst instances.  out: n_inst XYZZ results (device), complete on
+// tail.stream if a tail is given, else on s.
 template <class F>
 void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t pool_stride, XYZZ<F>* out,
-             MsmScratch& w, cudaStream_t s) {
+             MsmScratch& w, cudaStream_t s, const MsmTail& tail = MsmTail()) {
     if (n_inst == 0) return;
     size_t nbuckets = (size_t)n_inst * k.inst_stride;
     size_t max_entries = (size_t)n_inst * k.n_bases * k.nwin;
@@ -554,6 +576,13 @@ void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t po
         cudaEventDestroy(e1);
     }
 #endif
+#ifndef MB200_EMU
+    if (tail.on()) {
+        MB_CUDA(cudaEventRecord(tail.ev, s));
+        MB_CUDA(cudaStreamWaitEvent(tail.stream, tail.ev, 0));
+        s = tail.stream;
+    }
+#endif
     CombineArgs<F> ca;
     ca.nthreads = nbuckets;
     ca.partials = w.partials.as<XYZZ<F>>();
@@ -568,19 +597,24 @@ void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t po
     const XYZZ<F>* X = w.buckets.as<XYZZ<F>>();
     const XYZZ<F>* P = nullptr;
     int flip = 0;
-    uint32_t level = 0;
+    uint32_t level = 0, shift = 0;
+    // fan-in: wide at level 0 (many chunks: throughput-bound), narrow above it (few threads:
+    // the serial chain of 2 T additions per level is what the stream waits for)
+    static const uint32_t log_t0 = red_log_t("MB200_RED_LOG_T0", 3), log_t1 = red_log_t("MB200_RED_LOG_T1", 2);
     for (;;) {
+        const uint32_t log_t = level == 0 ? log_t0 : log_t1, T = 1u << log_t;
         RedArgs<F> ra;
         ra.X = X;
         ra.P = P;
         ra.n_weighted = n_w;
         ra.n_plain = n_p;
         ra.stride_in = stride_in;
-        ra.T = RED_T;
-        ra.n_wout = (n_w + RED_T - 1) / RED_T;
-        ra.n_out = ra.n_wout + (n_p + RED_T - 1) / RED_T;
+        ra.T = T;
+        ra.n_wout = (n_w + T - 1) / T;
+        ra.n_out = ra.n_wout + (n_p + T - 1) / T;
         ra.stride_out = ra.n_out;
-        ra.shift = level * RED_LOG_T;
+        ra.shift = shift;
+        shift += log_t;
         ra.level = level;
         ra.nthreads = (size_t)jobs * ra.n_out;
         w.lx[flip].ensure(ra.nthreads * sizeof(XYZZ<F>));

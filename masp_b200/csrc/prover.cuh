@@ -378,12 +378,15 @@ inline Params* params_load(const uint8_t* buf, size_t len, const uint8_t* a_aux_
 struct ProveCtx {  // one in-flight chunk: its streams and scratch
     cudaStream_t stream = 0;      // copies, NTT, H+L MSM, assembly
     cudaStream_t side[3] = {0, 0, 0};  // A, B1, B2 MSMs: they need only the staged witness, not the NTT
+    cudaStream_t tail[4] = {0, 0, 0, 0};  // high priority: reduction tails of A, B1, B2; [3] = H+L tail, assembly
+    bool split_tail = false;
     DevBuf abc, w0, w1, w2, w3, pool, flag, res_hl, res_a, res_b1, res_b2, cmul, proofs;
     DevBuf aff_a, aff_b, aff_c, ok;  // self-check: affine proof points, per-proof verdict
     MsmScratch msm, msm_side[3];
     bool have_stream = false;
 #ifndef MB200_EMU
     cudaEvent_t ev_inputs = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_acc[4] = {nullptr, nullptr, nullptr, nullptr}, ev_tail = nullptr;
 #endif
 };
 
@@ -470,20 +473,32 @@ inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, siz
     MB_CUDA(cudaEventRecord(x.ev_inputs, s));
     for (int i = 0; i < 3; ++i) MB_CUDA(cudaStreamWaitEvent(x.side[i], x.ev_inputs, 0));
 #endif
-    msm_run<Fp>(P.k_a, count, pl, P.pool_stride, x.res_a.as<G1XYZZ>(), x.msm_side[0], x.side[0]);
-    msm_run<Fp>(P.k_b1, count, pl, P.pool_stride, x.res_b1.as<G1XYZZ>(), x.msm_side[1], x.side[1]);
-    msm_run<Fp2>(P.k_b2, count, pl, P.pool_stride, x.res_b2.as<G2XYZZ>(), x.msm_side[2], x.side[2]);
+    MsmTail t_a, t_b1, t_b2, t_hl;
+    cudaStream_t fin = s;  // where the assembly runs
+#ifndef MB200_EMU
+    if (x.split_tail) {
+        t_a = {x.tail[0], x.ev_acc[0]};
+        t_b1 = {x.tail[1], x.ev_acc[1]};
+        t_b2 = {x.tail[2], x.ev_acc[2]};
+        t_hl = {x.tail[3], x.ev_acc[3]};
+        fin = x.tail[3];
+    }
+#endif
+    msm_run<Fp>(P.k_a, count, pl, P.pool_stride, x.res_a.as<G1XYZZ>(), x.msm_side[0], x.side[0], t_a);
+    msm_run<Fp>(P.k_b1, count, pl, P.pool_stride, x.res_b1.as<G1XYZZ>(), x.msm_side[1], x.side[1], t_b1);
+    msm_run<Fp2>(P.k_b2, count, pl, P.pool_stride, x.res_b2.as<G2XYZZ>(), x.msm_side[2], x.side[2], t_b2);
 
     h_pipeline(P.dom, count, (uint32_t)rows, x.abc.as<Fr>(), rows, x.pool.as<Fr>(), P.pool_stride, x.w0.as<Fr>(),
                x.w1.as<Fr>(), x.w2.as<Fr>(), x.w3.as<Fr>(), s);
-    msm_run<Fp>(P.k_hl, count, pl, P.pool_stride, x.res_hl.as<G1XYZZ>(), x.msm, s);
-    // join
+    msm_run<Fp>(P.k_hl, count, pl, P.pool_stride, x.res_hl.as<G1XYZZ>(), x.msm, s, t_hl);
+    // join: the assembly stream waits for the three side queries
 #ifndef MB200_EMU
     for (int i = 0; i < 3; ++i) {
-        MB_CUDA(cudaEventRecord(x.ev_side[i], x.side[i]));
-        MB_CUDA(cudaStreamWaitEvent(s, x.ev_side[i], 0));
+        MB_CUDA(cudaEventRecord(x.ev_side[i], x.split_tail ? x.tail[i] : x.side[i]));
+        MB_CUDA(cudaStreamWaitEvent(fin, x.ev_side[i], 0));
     }
 #endif
+    s = fin;
 
     CmulArgs ca{(size_t)count * 2, x.res_a.as<G1XYZZ>(), x.res_b1.as<G1XYZZ>(), pl, P.pool_stride, P.idx_r, P.idx_s,
                 x.cmul.as<G1XYZZ>()};
@@ -516,6 +531,12 @@ inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, siz
         launch_verify_proofs(va, s);
         copy_d2h(verify_out + first, x.ok.p, (size_t)count * 4, s);
     }
+#ifndef MB200_EMU
+    if (x.split_tail) {  // the chunk is done when its tail is: later work on this context queues behind it
+        MB_CUDA(cudaEventRecord(x.ev_tail, s));
+        MB_CUDA(cudaStreamWaitEvent(x.stream, x.ev_tail, 0));
+    }
+#endif
 }
 
 }  // namespace mb
