@@ -20,6 +20,7 @@
 // set: no per-window reduction and no doublings on the proving path.
 #pragma once
 #include "ec.cuh"
+#include "pair.cuh"
 
 namespace mb {
 
@@ -253,6 +254,7 @@ struct AccArgs {
     const uint32_t* order;  // thread -> task
     const uint32_t* ntasks;
     XYZZ<F>* partials;      // per task
+    const Affine<F>* direct;  // after pair rounds: the points themselves, bucket-sorted (else nullptr)
 };
 template <class F>
 MB_HD void acc_body(const AccArgs<F>& a, size_t tid) {
@@ -260,12 +262,18 @@ MB_HD void acc_body(const AccArgs<F>& a, size_t tid) {
     uint32_t t = a.order[tid];
     uint32_t n = a.task_len[t];
     XYZZ<F> acc = XYZZ<F>::inf();
-    const uint32_t* e = a.entries + a.task_start[t];
-    MB_NOUNROLL
-    for (uint32_t i = 0; i < n; ++i) {
-        uint32_t ent = e[i];
-        Affine<F> q = a.table[ent >> 1];
-        xyzz_madd(acc, q, (ent & 1) != 0);
+    if (a.direct) {
+        const Affine<F>* q = a.direct + a.task_start[t];
+        MB_NOUNROLL
+        for (uint32_t i = 0; i < n; ++i) xyzz_madd(acc, q[i], false);
+    } else {
+        const uint32_t* e = a.entries + a.task_start[t];
+        MB_NOUNROLL
+        for (uint32_t i = 0; i < n; ++i) {
+            uint32_t ent = e[i];
+            Affine<F> q = a.table[ent >> 1];
+            xyzz_madd(acc, q, (ent & 1) != 0);
+        }
     }
     a.partials[t] = acc;
 }
@@ -391,6 +399,8 @@ MB_K_RED_G2(msm_horner_g2, HornerArgs<Fp2>, horner_g2_body, 32)
 struct MsmScratch {
     DevBuf counts, offsets, cursor, partial, entries, buckets, lx[2], lp[2], order, ohist;
     DevBuf nseg, seg_off, task_bucket, task_start, task_len, ntasks, partials;
+    DevBuf pw[2], poff[2], pcnt[2];  // pair rounds: ping-pong point buffers and per-bucket layouts
+    DevBuf ppre, pprod, pinv, plast, pscr;  // pair rounds: prefixes, thread products, their inverses, scratch
 };
 
 struct MsmProfile {  // optional CUDA-event timing of the accumulate kernel
@@ -451,9 +461,51 @@ struct MsmTail {
 
 // Runs one class over n_inst instances.  out: n_inst XYZZ results (device), complete on
 // tail.stream if a tail is given, else on s.
+inline uint32_t msm_env(const char* name, uint32_t dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? (uint32_t)strtoul(v, nullptr, 10) : dflt;
+}
+// pair rounds in front of the accumulation (pair.cuh) and the instances per pass: the
+// intermediate points of a pass must fit the ping-pong buffers, so a batch is cut into passes
+// Default 0: measured on B200 the rounds cost more than they save (profiles/r01_pair_rounds_v2_sweep.jsonl:
+// 484 proofs/s without, 434 / 416 / 402 with 1 / 2 / 3 rounds) -- the two gathers per addition and the
+// prefix traffic make pair_b run at 0.8x of an XYZZ addition instead of the 0.5x its multiplications
+// suggest.  Kept as an opt-in experiment (MB200_PAIR_ROUNDS=n), covered by tests/test_emu.py.
+inline uint32_t msm_pair_rounds() {
+    static const uint32_t r = msm_env("MB200_PAIR_ROUNDS", 0);
+    return r > 8 ? 8 : r;
+}
+inline uint32_t msm_pair_b() {
+    static const uint32_t b = msm_env("MB200_PAIR_B", 32);
+    return b < 1 ? 1 : (b > 1024 ? 1024 : b);
+}
+inline uint32_t msm_pass_instances() {
+    static const uint32_t n = msm_env("MB200_PASS_INSTANCES", 16);
+    return n < 1 ? 1 : n;
+}
+
+template <class F>
+void msm_run_core(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t pool_stride, XYZZ<F>* out,
+                  MsmScratch& w, cudaStream_t s, const MsmTail& tail, uint32_t rounds);
+
 template <class F>
 void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t pool_stride, XYZZ<F>* out,
              MsmScratch& w, cudaStream_t s, const MsmTail& tail = MsmTail()) {
+    const uint32_t rounds = msm_pair_rounds();
+    if (rounds == 0) {
+        msm_run_core<F>(k, n_inst, pool, pool_stride, out, w, s, tail, 0);
+        return;
+    }
+    const uint32_t pass = msm_pass_instances();
+    for (uint32_t i0 = 0; i0 < n_inst; i0 += pass) {
+        uint32_t n = n_inst - i0 < pass ? n_inst - i0 : pass;
+        msm_run_core<F>(k, n, pool + (size_t)i0 * pool_stride * 8, pool_stride, out + i0, w, s, MsmTail(), rounds);
+    }
+}
+
+template <class F>
+void msm_run_core(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t pool_stride, XYZZ<F>* out,
+                  MsmScratch& w, cudaStream_t s, const MsmTail& tail, uint32_t rounds) {
     if (n_inst == 0) return;
     size_t nbuckets = (size_t)n_inst * k.inst_stride;
     size_t max_entries = (size_t)n_inst * k.n_bases * k.nwin;
@@ -494,6 +546,52 @@ void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t po
 
     launch_msm_scatter(da, s);
 
+    // pair rounds: halve every bucket `rounds` times with shared-inversion affine additions
+    const uint32_t* b_counts = w.counts.as<uint32_t>();
+    const uint32_t* b_offsets = w.offsets.as<uint32_t>();
+    const Affine<F>* direct = nullptr;
+    {
+        size_t slots = max_entries;  // bound on the index space of the round's input
+        for (uint32_t r = 0; r < rounds; ++r) {
+            slots = (slots + nbuckets + 1) / 2 + 1;
+            DevBuf& wout = w.pw[r & 1];
+            wout.ensure(slots * sizeof(Affine<F>));
+            w.poff[r & 1].ensure((nbuckets + 1) * 4);
+            w.pcnt[r & 1].ensure(nbuckets * 4);
+            PairArgs<F> pa;
+            pa.nbuckets = (uint32_t)nbuckets;
+            pa.off_in = b_offsets;
+            pa.cnt_in = b_counts;
+            pa.off_out = w.poff[r & 1].as<uint32_t>();
+            pa.cnt_out = w.pcnt[r & 1].as<uint32_t>();
+            pa.table = (const Affine<F>*)k.table;
+            pa.entries = r == 0 ? w.entries.as<uint32_t>() : nullptr;
+            pa.win = direct;
+            pa.wout = wout.as<Affine<F>>();
+            pa.nthreads = nbuckets + 1;
+            PairLaunch<F>::layout(pa, s);
+            const uint32_t B = msm_pair_b();
+            const size_t T = (slots + B - 1) / B;
+            w.ppre.ensure((size_t)B * T * sizeof(F));
+            w.pprod.ensure(T * sizeof(F));
+            w.pinv.ensure(T * sizeof(F));
+            w.plast.ensure(T * 4);
+            w.pscr.ensure(binv_scratch_elems(T) * sizeof(F));
+            pa.B = B;
+            pa.nthreads = T;
+            pa.gpre = w.ppre.as<F>();
+            pa.gprod = w.pprod.as<F>();
+            pa.ginv = w.pinv.as<F>();
+            pa.glast = w.plast.as<uint32_t>();
+            PairLaunch<F>::pa(pa, s);
+            batch_inverse_device<F>(w.pprod.as<F>(), T, w.pinv.as<F>(), w.pscr.as<F>(), s);
+            PairLaunch<F>::pb(pa, s);
+            b_offsets = pa.off_out;
+            b_counts = pa.cnt_out;
+            direct = pa.wout;
+        }
+    }
+
     // tasks: segments of at most SEG_LEN entries, longest first
     size_t max_tasks = nbuckets + max_entries / SEG_LEN + 1;
     if (max_tasks >= (1ull << 32)) fail(MB200_EINVAL, "too many buckets%s (%ld)", "", (long)nbuckets);
@@ -508,8 +606,8 @@ void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t po
     w.partials.ensure(max_tasks * sizeof(XYZZ<F>));
     SegArgs ga;
     ga.nthreads = nbuckets;
-    ga.counts = w.counts.as<uint32_t>();
-    ga.offsets = w.offsets.as<uint32_t>();
+    ga.counts = b_counts;
+    ga.offsets = b_offsets;
     ga.nseg = w.nseg.as<uint32_t>();
     ga.seg_off = w.seg_off.as<uint32_t>();
     ga.task_bucket = w.task_bucket.as<uint32_t>();
@@ -554,6 +652,7 @@ void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t po
     aa.order = w.order.as<uint32_t>();
     aa.ntasks = w.ntasks.as<uint32_t>();
     aa.partials = w.partials.as<XYZZ<F>>();
+    aa.direct = direct;
 #ifndef MB200_EMU
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_msm_profile.enabled) {

@@ -90,3 +90,40 @@ def test_local_tx_prover_surface(emu, oracle):
     # create_random_proof draws r, s itself: two calls must differ, both must be 192 bytes
     p1, p2 = prover.spend_proof(spends[0]), prover.spend_proof(spends[0])
     assert len(p1) == len(p2) == 192 and p1 != p2
+
+
+def test_msm_special_bases(emu, oracle):
+    """Repeated bases (P + P inside a pair), negated pairs (P + (-P)), identities:
+    the shared-inversion pair rounds (csrc/pair.cuh) must take the tangent, drop
+    the cancelling pair and pass infinities through, like the XYZZ accumulator."""
+    P_MOD = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+    logs = syn.fr_uniform(syn.MASTER_SEED, 12, 8)
+    bases = oracle.g1_gen_mul(syn.limbs_to_bytes(logs), 8)
+    pts = [bases[96 * i:96 * (i + 1)] for i in range(8)]
+    neg = lambda p: p[:48] + ((P_MOD - int.from_bytes(p[48:], "big")) % P_MOD).to_bytes(48, "big")
+    inf = bytes([0x40]) + bytes(95)
+    seq = [pts[0], pts[0], pts[0], neg(pts[0]), pts[1], neg(pts[1]), inf, pts[2], pts[2], inf, pts[3], pts[3], pts[3], pts[3]]
+    b = b"".join(seq)
+    for scalars in ([5] * len(seq), [syn.R_INT - 1] * len(seq), [1] * len(seq), list(range(len(seq))),
+                    [7, 7, 9, 7, 3, 3, 5, 1, 1, 0, 2, 2, 2, 2]):
+        assert emu.msm_g1(b, ib(scalars), len(seq)) == oracle.msm_g1(b, ib(scalars), len(seq)), scalars
+    b2 = oracle.g2_gen_mul(syn.limbs_to_bytes(logs[:3]), 3)
+    q = [b2[192 * i:192 * (i + 1)] for i in range(3)]
+    seq2 = [q[0], q[0], q[1], q[1], q[1], q[2], q[0]]
+    for scalars in ([3] * 7, [1] * 7, [9, 9, 4, 4, 4, 1, 9]):
+        assert emu.msm_g2(b"".join(seq2), ib(scalars), 7) == oracle.msm_g2(b"".join(seq2), ib(scalars), 7), scalars
+
+
+@pytest.mark.slow
+def test_pair_rounds_variant():
+    """The opt-in batched-affine pair rounds (csrc/pair.cuh, MB200_PAIR_ROUNDS) give the
+    same bytes as the default schedule: the MSM and prover tests again in a child
+    process with the rounds switched on (the knob is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, MB200_PAIR_ROUNDS="3", MB200_PASS_INSTANCES="2", MB200_PAIR_B="5")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu.py"), "-x", "-q", "-k",
+                        "test_msm or test_prove_batch_chunked"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:]
