@@ -264,6 +264,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline budget on rank 0")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-circuit-path", action="store_true")
+    ap.add_argument("--verify", action="store_true",
+                    help="run the Groth16 check on every proof inside the timed region (the reference's "
+                         "verify_proof after create_random_proof, sapling/prover.rs:148)")
     ap.add_argument("--circuit-batch", type=int, default=64, help="real-witness leg: proofs per round")
     ap.add_argument("--circuit-rounds", type=int, default=12)
     args = ap.parse_args()
@@ -285,6 +288,9 @@ def main():
         pv.set_option("chunk", args.chunk)
     if args.streams:
         pv.set_option("streams", args.streams)
+    if args.verify:
+        # synthetic keys and witnesses do not verify: count, do not fail (same kernel, same cost)
+        pv.set_option("verify", 2)
 
     t_setup = time.perf_counter()
     key = pv.params_synthesize(shape)
@@ -397,6 +403,7 @@ def main():
                         "synthetic witnesses (%.1f%% boolean aux)" % (shape.name, shape.n_constraints, rows, shape.log_m, B,
                                                                     100.0 * shape.n_bool / shape.n_aux),
             "circuit": shape.name, "batch_per_gpu": B, "parallelism": "proof-sharded x%d, no collective" % world,
+            "self_check": "verify_proof on the device for every proof" if args.verify else "off",
             "l2": "inputs per step (%.2f GB) are larger than the 126 MB L2" % (h2d / 1e9),
             "pipelining": "steps are streamed (mb200_prove_submit / mb200_prove_wait, <= 2 batches in flight); "
                           "the timed region is bracketed by barrier + synchronize",
@@ -407,6 +414,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 192,
                 "ms_per_step": 1e3 * wall_e2e / args.steps},
         "gpu_launches": int(launches),
+        "self_check": ({"verified": int(pv.get_counter("verified")), "failed": int(pv.get_counter("verify_failed")),
+                        "note": "synthetic keys / witnesses cannot verify; the count shows the kernel ran"}
+                       if args.verify else None),
         "clocks": sampler.summary(),
         "roofline": {
             "bound": "hbm", "kernel": "msm_accumulate_g1/g2 (bucket accumulation, all four queries)",

@@ -169,7 +169,8 @@ int mb200_prove_batch_witness(const mb200_params* p, size_t n_proofs, const uint
  * proof.  Two forms:
  *   - mb200_set_option("verify", 1): every prove call checks its own proofs with the key's
  *     verifying key and the witnesses' public inputs before returning them; a failure makes the
- *     call return MB200_EVERIFY (the reference's Err(())).
+ *     call return MB200_EVERIFY (the reference's Err(())).  Value 2 runs the same check but only
+ *     counts (counters "verified", "verify_failed"): for measuring its cost on synthetic keys.
  *   - mb200_verify_batch: n proofs given as uncompressed points A (96) | B (192) | C (96) and
  *     n x n_inputs public-input scalars (inputs[0] = 1); ok_out[i] = 1 iff
  *     e(A,B) = e(alpha,beta) e(sum x_i IC_i, gamma) e(C, delta). */

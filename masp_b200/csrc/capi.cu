@@ -29,7 +29,9 @@ struct State {
     cudaStream_t main = 0;
     std::vector<ProveCtx> ctxs;
     uint32_t chunk = 64;
-    bool verify = false;  // option "verify": run the Groth16 check on every proof before returning it
+    int verify = 0;  // option "verify": 1 = check every proof before returning it (failure = MB200_EVERIFY),
+                     // 2 = check and only count the failures (counter "verify_failed"; for measuring the cost)
+    unsigned long long verify_failed = 0, verified = 0;
     std::map<unsigned, NttCache*> ntt;
     MsmScratch msm;
     std::mutex mu;
@@ -253,9 +255,14 @@ static void prove_wait(uint64_t id) {
         if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
         memcpy(t->out, t->staged, t->n_proofs * 192);
         if (t->verdicts)
-            for (size_t i = 0; i < t->n_proofs; ++i)
-                if (!t->verdicts[i])
-                    fail(MB200_EVERIFY, "proof %s%ld does not satisfy the verification equation", "", (long)i);
+            for (size_t i = 0; i < t->n_proofs; ++i) {
+                g.verified++;
+                if (!t->verdicts[i]) {
+                    g.verify_failed++;
+                    if (g.verify == 1)
+                        fail(MB200_EVERIFY, "proof %s%ld does not satisfy the verification equation", "", (long)i);
+                }
+            }
     } catch (...) {
         ticket_destroy(t);
         throw;
@@ -775,7 +782,7 @@ int mb200_set_option(const char* name, long value) {
         if (value < 1 || value > 8) fail(MB200_EINVAL, "streams out of range%s (%ld)", "", value);
         set_ctx_count((size_t)value);
     } else if (!strcmp(name, "verify")) {
-        g.verify = value != 0;
+        g.verify = (int)value;
     } else if (!strcmp(name, "profile")) {
         g_msm_profile.enabled = value != 0;
         g_msm_profile.acc_ms = 0;
@@ -795,6 +802,8 @@ int mb200_get_counter(const char* name, double* value) {
     else if (!strcmp(name, "acc_us")) *value = g_msm_profile.acc_ms * 1000.0;
     else if (!strcmp(name, "acc_bytes")) *value = (double)g_msm_profile.acc_entries_bound;
     else if (!strcmp(name, "last_batch_us")) *value = g.last_batch_ms * 1000.0;
+    else if (!strcmp(name, "verified")) *value = (double)g.verified;
+    else if (!strcmp(name, "verify_failed")) *value = (double)g.verify_failed;
     else fail(MB200_EINVAL, "unknown counter %s", name);
     MB_API_END
 }
@@ -812,6 +821,14 @@ int mb200_selftest(void) {
         a.g1 = g1_generator_host();
         a.g2 = g2_generator_host();
         launch_selftest_kernel(a, g.main);
+        // pairing: x-chain final exponentiation against the plain power, Frobenius consistency
+        DevBuf gens(sizeof(G1Affine) + sizeof(G2Affine));
+        G1Affine hg1 = g1_generator_host();
+        G2Affine hg2 = g2_generator_host();
+        copy_h2d(gens.p, &hg1, sizeof hg1, g.main);
+        copy_h2d((char*)gens.p + sizeof(G1Affine), &hg2, sizeof hg2, g.main);
+        PairSelfTestArgs pa{1, gens.as<G1Affine>(), (const G2Affine*)((char*)gens.p + sizeof(G1Affine)), d.as<uint32_t>()};
+        launch_pair_selftest(pa, g.main);
         copy_d2h(&bad, d.p, 4, g.main);
         stream_sync(g.main);
         return (int)bad;

@@ -12,8 +12,9 @@
 // optimal-ate Miller loop over |x| = 0xd201000000010000 with the G2 point kept
 // in Jacobian coordinates (no inversions; every line is scaled by an Fp2 factor,
 // which the final exponentiation kills); final exponentiation = easy part by
-// conjugation, one inversion and the p^2-Frobenius, hard part as a plain power
-// (p^4 - p^2 + 1) / r.
+// conjugation, one inversion and the p^2-Frobenius, hard part (cubed) by the
+// BLS12 x-chain: five powers by |x| and two Frobenius maps, pinned against the
+// plain power (p^4 - p^2 + 1) / r by the device self-test.
 #pragma once
 #include "ec.cuh"
 
@@ -39,7 +40,28 @@ struct PairConst {
         for (int i = 0; i < 12; ++i) r.v[i] = t[k - 1][i];
         return r;
     }
-    // (p^4 - p^2 + 1) / r, 1268 bits, little-endian words
+    // xi^((p - 1) k / 6) for k = 1..5, in Fp2 (Montgomery form): the p-Frobenius of the basis w^k
+    MB_HD static Fp2 g(int k) {
+        constexpr uint32_t t[5][2][12] = {
+            {{0xb319d465u, 0x07089552u, 0xb50a8313u, 0xc6695f92u, 0xd117228fu, 0x97e83cccu, 0xb2dc29eeu, 0xa35baecau, 0x5daace4du, 0x1ce393eau, 0xb0fb66ebu, 0x08f2220fu},
+             {0x4ce5d646u, 0xb2f66aadu, 0xfc497cecu, 0x5842a06bu, 0x2599d394u, 0xcf4895d4u, 0x40a8e8d0u, 0xc11b9cbau, 0xe5a0de89u, 0x2e3813cbu, 0x88847fafu, 0x110eefdau}},
+            {{0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0},
+             {0x8671f071u, 0xcd03c9e4u, 0x1fcda5d2u, 0x5dab2246u, 0xd3851b95u, 0x587042afu, 0x01bacb9eu, 0x8eb60ebeu, 0x83d050d2u, 0x03f97d6eu, 0x54638741u, 0x18f02065u}},
+            {{0x5aa30fdau, 0x7bcfa7a2u, 0x2a927e7cu, 0xdc17dec1u, 0x6b4ebef1u, 0x2f088dd8u, 0xda74d4a7u, 0xd1ca2087u, 0x96cebc1du, 0x2da25966u, 0xbbfd87d2u, 0x0e2b7eedu},
+             {0x5aa30fdau, 0x7bcfa7a2u, 0x2a927e7cu, 0xdc17dec1u, 0x6b4ebef1u, 0x2f088dd8u, 0xda74d4a7u, 0xd1ca2087u, 0x96cebc1du, 0x2da25966u, 0xbbfd87d2u, 0x0e2b7eedu}},
+            {{0x867545c3u, 0x890dc9e4u, 0x3285a5d5u, 0x2af32253u, 0x309b7e2cu, 0x50880866u, 0x7e881024u, 0xa20d1b8cu, 0xe2db9068u, 0x14e4f04fu, 0x1564853au, 0x14e56d3fu},
+             {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}},
+            {{0x0dbce43fu, 0x82d83cf5u, 0xdf9d018fu, 0xa2813e53u, 0x3c65e181u, 0xc6f0caa5u, 0x8d50fe95u, 0x7525cf52u, 0xf4798a6bu, 0x4a85ed50u, 0x6cf8eebdu, 0x171da0fdu},
+             {0xf242c66cu, 0x3726c30au, 0xd1b6fe70u, 0x7c2ac1aau, 0xba4b14a2u, 0xa04007fbu, 0x66341429u, 0xef517c32u, 0x4ed2226bu, 0x0095ba65u, 0xcc86f7ddu, 0x02e370ecu}}};
+        Fp2 r;
+        for (int i = 0; i < 12; ++i) {
+            r.c0.v[i] = t[k - 1][0][i];
+            r.c1.v[i] = t[k - 1][1][i];
+        }
+        return r;
+    }
+    // (p^4 - p^2 + 1) / r, 1268 bits, little-endian words (the plain-power form of the hard part; the
+    // product path uses the x-chain below, this constant pins it in the self-test)
     MB_HD static uint32_t hard(int i) {
         constexpr uint32_t t[40] = {
             0x38e3ba79u, 0xe516c3f4u, 0xe208ccf1u, 0xfa9912aau, 0x335d5b68u, 0x905ce937u, 0xb0dea236u, 0xc71a2629u,
@@ -106,6 +128,28 @@ MB_COLD Fp12 f12_frob2(const Fp12& a) {
     r.c1.c0 = f2_scale(a.c1.c0, PairConst::w(1));
     r.c1.c1 = f2_scale(a.c1.c1, PairConst::w(3));
     r.c1.c2 = f2_scale(a.c1.c2, PairConst::w(5));
+    return r;
+}
+// a^p: conjugate the Fp2 coefficients, the basis element w^k picks up xi^((p-1) k / 6)
+MB_HD Fp2 f2_conj(const Fp2& a) { return {a.c0, Fp::neg(a.c1)}; }
+MB_COLD Fp12 f12_frob1(const Fp12& a) {
+    Fp12 r;
+    r.c0.c0 = f2_conj(a.c0.c0);
+    r.c0.c1 = f2_mul(f2_conj(a.c0.c1), PairConst::g(2));
+    r.c0.c2 = f2_mul(f2_conj(a.c0.c2), PairConst::g(4));
+    r.c1.c0 = f2_mul(f2_conj(a.c1.c0), PairConst::g(1));
+    r.c1.c1 = f2_mul(f2_conj(a.c1.c1), PairConst::g(3));
+    r.c1.c2 = f2_mul(f2_conj(a.c1.c2), PairConst::g(5));
+    return r;
+}
+// a^|x|
+MB_COLD Fp12 f12_pow_x(const Fp12& a) {
+    Fp12 r = a;
+    MB_NOUNROLL
+    for (int bit = 62; bit >= 0; --bit) {
+        r = f12_mul(r, r);
+        if ((PairConst::X >> bit) & 1) r = f12_mul(r, a);
+    }
     return r;
 }
 MB_HD bool f12_is_one(const Fp12& a) {
@@ -183,17 +227,33 @@ MB_COLD Fp12 miller_multi(const G1Affine* ps, const G2Affine* qs, int n) {
     }
     return f12_conj(f);
 }
-MB_COLD Fp12 final_exponentiation(const Fp12& f) {
+MB_COLD Fp12 final_exp_easy(const Fp12& f) {
     Fp12 f1 = f12_mul(f12_conj(f), f12_inv(f));  // f^(p^6 - 1)
-    Fp12 f2 = f12_mul(f12_frob2(f1), f1);        // ^(p^2 + 1)
+    return f12_mul(f12_frob2(f1), f1);           // ^(p^2 + 1): unitary from here on, inverse = conjugate
+}
+// The hard part as a plain power (p^4 - p^2 + 1) / r: 1268 squarings.  Reference form, used by
+// the self-test to pin the chain below.
+MB_COLD Fp12 final_exp_hard_plain(const Fp12& e) {
     Fp12 r = f12_one();
     MB_NOUNROLL
     for (int i = PairConst::HARD_BITS - 1; i >= 0; --i) {
         r = f12_mul(r, r);
-        if ((PairConst::hard(i >> 5) >> (i & 31)) & 1) r = f12_mul(r, f2);
+        if ((PairConst::hard(i >> 5) >> (i & 31)) & 1) r = f12_mul(r, e);
     }
     return r;
 }
+// The hard part cubed, by the BLS12 identity
+//     3 (p^4 - p^2 + 1) / r = (x - 1)^2 (x + p) (x^2 + p^2 - 1) + 3,
+// five powers by |x| (x < 0: a^x = conj(a^|x|) on unitary a) and two Frobenius maps.  Cubing is
+// harmless for the comparison with one: the result lies in the order-r subgroup and 3 does not divide r.
+MB_COLD Fp12 final_exp_hard_cubed(const Fp12& e) {
+    Fp12 a = f12_conj(f12_mul(f12_pow_x(e), e));      // e^(x - 1)
+    a = f12_conj(f12_mul(f12_pow_x(a), a));           // e^((x - 1)^2)
+    Fp12 b = f12_mul(f12_conj(f12_pow_x(a)), f12_frob1(a));                               // a^(x + p)
+    Fp12 c = f12_mul(f12_mul(f12_pow_x(f12_pow_x(b)), f12_frob2(b)), f12_conj(b));        // b^(x^2 + p^2 - 1)
+    return f12_mul(c, f12_mul(f12_mul(e, e), e));
+}
+MB_COLD Fp12 final_exponentiation(const Fp12& f) { return final_exp_hard_cubed(final_exp_easy(f)); }
 
 // ---------------------------------------------------------------------------
 // kernels
@@ -253,10 +313,43 @@ MB_HD void verify_body(const VerifyArgs& a, size_t tid) {
     a.ok[tid] = f12_is_one(final_exponentiation(f)) ? 1u : 0u;
 }
 
+// self-test: the x-chain against the plain power, Frobenius maps against plain powers' structure
+struct PairSelfTestArgs {
+    size_t nthreads;  // 1
+    const G1Affine* g1;
+    const G2Affine* g2;
+    uint32_t* mismatches;
+};
+MB_HD void pair_selftest_body(const PairSelfTestArgs& a, size_t) {
+    uint32_t bad = 0;
+    Fp12 f = miller_multi(a.g1, a.g2, 1);
+    Fp12 e = final_exp_easy(f);
+    Fp12 plain = final_exp_hard_plain(e);
+    Fp12 cubed = f12_mul(f12_mul(plain, plain), plain);
+    Fp12 chain = final_exp_hard_cubed(e);
+    Fp6 d0 = f6_sub(cubed.c0, chain.c0), d1 = f6_sub(cubed.c1, chain.c1);
+    if (!(d0.c0.is_zero() && d0.c1.is_zero() && d0.c2.is_zero() && d1.c0.is_zero() && d1.c1.is_zero() && d1.c2.is_zero())) bad++;
+    if (f12_is_one(plain)) bad++;                       // e(G1, G2) is not degenerate
+    // unitary after the easy part: e * conj(e) = 1
+    if (!f12_is_one(f12_mul(e, f12_conj(e)))) bad++;
+    // p^2-Frobenius twice more is the p^6-Frobenius = conjugation on Fp12
+    Fp12 c = f12_frob2(f12_frob2(f12_frob2(f)));
+    Fp12 cj = f12_conj(f);
+    Fp6 e0 = f6_sub(c.c0, cj.c0), e1 = f6_sub(c.c1, cj.c1);
+    if (!(e0.c0.is_zero() && e0.c1.is_zero() && e0.c2.is_zero() && e1.c0.is_zero() && e1.c1.is_zero() && e1.c2.is_zero())) bad++;
+    // p-Frobenius twice is the p^2-Frobenius
+    Fp12 u = f12_frob1(f12_frob1(f)), v = f12_frob2(f);
+    Fp6 g0 = f6_sub(u.c0, v.c0), g1 = f6_sub(u.c1, v.c1);
+    if (!(g0.c0.is_zero() && g0.c1.is_zero() && g0.c2.is_zero() && g1.c0.is_zero() && g1.c1.is_zero() && g1.c2.is_zero())) bad++;
+    if (bad) MB_ATOMIC_ADD(a.mismatches, bad);
+}
+
 #ifdef MB_DEFINE_PAIR
+MB_KERNEL_DEF(pair_selftest, PairSelfTestArgs, pair_selftest_body, 32)
 MB_KERNEL_DEF(pair_prep, PairPrepArgs, pair_prep_body, 32)
 MB_KERNEL_DEF(verify_proofs, VerifyArgs, verify_body, 32)
 #else
+MB_KERNEL_DECL(pair_selftest, PairSelfTestArgs)
 MB_KERNEL_DECL(pair_prep, PairPrepArgs)
 MB_KERNEL_DECL(verify_proofs, VerifyArgs)
 #endif
