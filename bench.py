@@ -120,7 +120,7 @@ def make_batch(shape, batch, first_index, torch, pv):
     return host, dev
 
 
-def circuit_path(pv, key, shape, n, rounds, seed=20261017):
+def circuit_path(pv, key, shape, n, rounds, seed=20261017, torch=None):
     """The drop-in call a TxProver makes, measured: real Spend witnesses ->
     product-side witness generation on the host cores (mb200_circuit_synthesize)
     -> only inputs + aux cross PCIe -> rows on the device (r1cs_eval) -> proof.
@@ -153,9 +153,16 @@ def circuit_path(pv, key, shape, n, rounds, seed=20261017):
     r_b, s_b = to_b(rnd.randrange(syn.R_INT) for _ in range(n)), to_b(rnd.randrange(syn.R_INT) for _ in range(n))
     import numpy as np
     outs = [np.empty(192 * n, dtype=np.uint8) for _ in range(rounds)]
+    # witnesses are generated straight into pinned memory (a ring of four buffer pairs), so the
+    # host-to-device copies of a submission are asynchronous
+    def pinned(nbytes):
+        if torch is None:
+            return np.empty(nbytes, dtype=np.uint8)
+        return torch.empty(nbytes, dtype=torch.uint8).pin_memory().numpy()
+    ring = [(pinned(n * circ.n_inputs * 32), pinned(n * circ.n_aux * 32)) for _ in range(4)]
     # each stage alone
     t0 = time.perf_counter()
-    inputs, aux = circ.synthesize(packed[0], numpy=True)
+    inputs, aux = circ.synthesize(packed[0], out=ring[0])
     t_synth = time.perf_counter() - t0
     pv.prove_wait(pv.prove_submit_witness(params, n, inputs, aux, r_b, s_b, outs[0]))  # warm-up
     t0 = time.perf_counter()
@@ -165,11 +172,14 @@ def circuit_path(pv, key, shape, n, rounds, seed=20261017):
     # pipelined: a host thread synthesises batch after batch; this thread keeps up
     # to two batches in flight on the device (submit / wait)
     import queue
-    q = queue.Queue(maxsize=2)
+    q = queue.Queue(maxsize=1)
+    free = queue.Queue()
+    for b in ring:
+        free.put(b)
 
     def producer():
         for k in range(rounds):
-            q.put(circ.synthesize(packed[k], numpy=True))
+            q.put(circ.synthesize(packed[k], out=free.get()))
     t0 = time.perf_counter()
     th = threading.Thread(target=producer)
     th.start()
@@ -180,10 +190,11 @@ def circuit_path(pv, key, shape, n, rounds, seed=20261017):
         tickets.append(pv.prove_submit_witness(params, n, inp_k, aux_k, r_b, s_b, outs[k]))
         if len(tickets) > 2:
             pv.prove_wait(tickets.pop(0))
-            keep.pop(0)
+            free.put(keep.pop(0))
             done += n
     while tickets:
         pv.prove_wait(tickets.pop(0))
+        free.put(keep.pop(0))
         done += n
     th.join()
     t_pipe = time.perf_counter() - t0
@@ -434,7 +445,7 @@ def main():
 
     if world == 1 and not args.no_circuit_path:
         try:
-            line["circuit_path"] = circuit_path(pv, key, shape, args.circuit_batch, args.circuit_rounds)
+            line["circuit_path"] = circuit_path(pv, key, shape, args.circuit_batch, args.circuit_rounds, torch=torch)
         except Exception as e:  # reported, never silently dropped
             line["circuit_path"] = {"error": repr(e)}
 

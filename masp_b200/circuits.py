@@ -149,7 +149,7 @@ class Circuit:
         vals = [int.from_bytes(coef.raw[32 * i:32 * i + 32], "little") for i in range(nnz)]
         return list(rp), list(col)[:nnz], vals
 
-    def synthesize(self, instances, threads=0, numpy=False):
+    def synthesize(self, instances, threads=0, numpy=False, out=None):
         """Witness half of Circuit::synthesize for a list of instances (or packed
         witness bytes): returns (inputs, aux), n x n_inputs / n x n_aux scalars, as
         bytes -- or, with numpy=True, as uint8 arrays written in place (no copies:
@@ -160,8 +160,14 @@ class Circuit:
         for w in ws:
             if len(w) != self.witness_bytes:
                 raise ValueError("witness has %d bytes, this circuit takes %d" % (len(w), self.witness_bytes))
-        inp = np.empty(max(1, n * self.n_inputs * 32), dtype=np.uint8)
-        aux = np.empty(max(1, n * self.n_aux * 32), dtype=np.uint8)
+        if out is not None:  # caller-owned uint8 arrays, e.g. views of pinned memory
+            inp, aux = out
+            if inp.nbytes < n * self.n_inputs * 32 or aux.nbytes < n * self.n_aux * 32:
+                raise ValueError("output buffers too small")
+            numpy = True
+        else:
+            inp = np.empty(max(1, n * self.n_inputs * 32), dtype=np.uint8)
+            aux = np.empty(max(1, n * self.n_aux * 32), dtype=np.uint8)
         check(_lib.lib().mb200_circuit_synthesize(self._h, n, b"".join(ws), inp.ctypes.data_as(ctypes.c_char_p),
                                                   aux.ctypes.data_as(ctypes.c_char_p), threads))
         inp, aux = inp[:n * self.n_inputs * 32], aux[:n * self.n_aux * 32]

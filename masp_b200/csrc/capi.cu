@@ -32,6 +32,8 @@ struct State {
     int verify = 0;  // option "verify": 1 = check every proof before returning it (failure = MB200_EVERIFY),
                      // 2 = check and only count the failures (counter "verify_failed"; for measuring the cost)
     unsigned long long verify_failed = 0, verified = 0;
+    cudaStream_t vstream[4] = {0, 0, 0, 0};  // the self-check's streams (round robin over chunks)
+    size_t next_v = 0;
     std::map<unsigned, NttCache*> ntt;
     MsmScratch msm;
     std::mutex mu;
@@ -151,13 +153,40 @@ static void check_scalars_dev(const Fr* base, size_t per_row, size_t row_stride,
     launch_validate_scalars(va, s);
 }
 
+// Buffers a batch needs for its lifetime.  They are recycled across batches: cudaMalloc /
+// cudaFree / cudaFreeHost synchronise the whole device, which would serialise batches that are
+// meant to overlap (submit k+1 while k is still running, wait k while k+1 runs).
+struct TicketRes {
+    uint8_t* staged = nullptr;     // pinned: proofs land here
+    size_t staged_cap = 0;
+    uint32_t* verdicts = nullptr;  // pinned: per-proof result of the self-check (option "verify")
+    size_t verdicts_cap = 0;
+    DevBuf v_a, v_b, v_c, v_in, v_ok;  // self-check inputs / verdicts of this batch (device)
+    DevBuf flag;                   // set by the canonical-scalar checks of this batch
+    ~TicketRes() {
+        host_free_pinned(staged);
+        host_free_pinned(verdicts);
+    }
+};
+static std::vector<TicketRes*> g_res_free;
+static TicketRes* res_acquire() {
+    if (g_res_free.empty()) return new TicketRes();
+    TicketRes* r = g_res_free.back();
+    g_res_free.pop_back();
+    return r;
+}
+
 // One submitted batch: everything needed to finish it later.
 struct Ticket {
-    uint8_t* staged = nullptr;  // pinned: proofs land here
-    uint32_t* verdicts = nullptr;  // pinned: per-proof result of the self-check (option "verify")
+    TicketRes* res = nullptr;
+    uint8_t* staged = nullptr;     // = res->staged
+    uint32_t* verdicts = nullptr;  // = res->verdicts when the self-check is on
+#ifndef MB200_EMU
+    cudaEvent_t ev_v[4] = {nullptr, nullptr, nullptr, nullptr};
+#endif
     uint8_t* out = nullptr;     // caller's buffer
     size_t n_proofs = 0;
-    DevBuf flag;                // set by the canonical-scalar checks of this batch
+    uint32_t* flag = nullptr;   // = res->flag
 #ifndef MB200_EMU
     cudaEvent_t ev0 = nullptr;
     std::vector<cudaEvent_t> ev1;
@@ -171,11 +200,12 @@ static void ticket_destroy(Ticket* t) {
     if (!t) return;
 #ifndef MB200_EMU
     if (t->ev0) cudaEventDestroy(t->ev0);
+    for (auto& e : t->ev_v)
+        if (e) cudaEventDestroy(e);
     for (auto& e : t->ev1)
         if (e) cudaEventDestroy(e);
 #endif
-    host_free_pinned(t->staged);
-    host_free_pinned(t->verdicts);
+    if (t->res) g_res_free.push_back(t->res);
     delete t;
 }
 
@@ -197,10 +227,38 @@ static uint64_t prove_submit(const Params& P, size_t n_proofs, size_t rows, cons
     try {
         t->n_proofs = n_proofs;
         t->out = proofs_out;
-        t->staged = (uint8_t*)host_alloc_pinned(n_proofs * 192);
-        if (g.verify) t->verdicts = (uint32_t*)host_alloc_pinned(n_proofs * 4);
-        t->flag.alloc(4);
-        dev_memset(t->flag.p, 0, 4, g.main);
+        TicketRes* R = t->res = res_acquire();
+        if (R->staged_cap < n_proofs * 192) {
+            host_free_pinned(R->staged);
+            R->staged = nullptr;
+            R->staged = (uint8_t*)host_alloc_pinned(n_proofs * 192);
+            R->staged_cap = n_proofs * 192;
+        }
+        t->staged = R->staged;
+        VerifySink sink;
+        if (g.verify) {
+            if (R->verdicts_cap < n_proofs * 4) {
+                host_free_pinned(R->verdicts);
+                R->verdicts = nullptr;
+                R->verdicts = (uint32_t*)host_alloc_pinned(n_proofs * 4);
+                R->verdicts_cap = n_proofs * 4;
+            }
+            t->verdicts = R->verdicts;
+            R->v_a.ensure(n_proofs * sizeof(G1Affine));
+            R->v_b.ensure(n_proofs * sizeof(G2Affine));
+            R->v_c.ensure(n_proofs * sizeof(G1Affine));
+            R->v_in.ensure(n_proofs * (size_t)P.n_inputs * 32);
+            R->v_ok.ensure(n_proofs * 4);
+            sink.a = R->v_a.as<G1Affine>();
+            sink.b = R->v_b.as<G2Affine>();
+            sink.c = R->v_c.as<G1Affine>();
+            sink.inputs = R->v_in.as<uint32_t>();
+            sink.ok_dev = R->v_ok.as<uint32_t>();
+            sink.ok_host = t->verdicts;
+        }
+        R->flag.ensure(4);
+        t->flag = R->flag.as<uint32_t>();
+        dev_memset(t->flag, 0, 4, g.main);
 #ifndef MB200_EMU
         // every chunk stream starts after `ev0` (and so after the flag reset)
         t->ev1.assign(g.ctxs.size(), nullptr);
@@ -212,14 +270,22 @@ static uint64_t prove_submit(const Params& P, size_t n_proofs, size_t rows, cons
         for (size_t first = 0; first < n_proofs; first += g.chunk) {
             uint32_t count = (uint32_t)std::min<size_t>(g.chunk, n_proofs - first);
             ProveCtx& x = g.ctxs[g_next_ctx++ % g.ctxs.size()];
-            prove_chunk(P, x, in, first, count, rows, t->staged, t->verdicts);
+#ifndef MB200_EMU
+            sink.stream = g.vstream[g.next_v++ % 4];
+#endif
+            prove_chunk(P, x, in, first, count, rows, t->staged, sink);
             // canonical-scalar check on what was just staged (abc and aux..s of the pool)
-            check_scalars_dev(x.abc.as<Fr>(), (size_t)count * 3 * rows, 0, 1, t->flag.as<uint32_t>(), x.stream);
+            check_scalars_dev(x.abc.as<Fr>(), (size_t)count * 3 * rows, 0, 1, t->flag, x.stream);
             check_scalars_dev(x.pool.as<Fr>() + P.idx_aux, P.idx_one - P.idx_aux, P.pool_stride, count,
-                              t->flag.as<uint32_t>(), x.stream);
+                              t->flag, x.stream);
         }
 #ifndef MB200_EMU
         for (size_t i = 0; i < g.ctxs.size(); ++i) MB_CUDA(cudaEventRecord(t->ev1[i], g.ctxs[i].stream));
+        if (g.verify)
+            for (int i = 0; i < 4; ++i) {
+                MB_CUDA(cudaEventCreateWithFlags(&t->ev_v[i], cudaEventDisableTiming));
+                MB_CUDA(cudaEventRecord(t->ev_v[i], g.vstream[i]));
+            }
 #endif
     } catch (...) {
 #ifndef MB200_EMU
@@ -250,7 +316,11 @@ static void prove_wait(uint64_t id) {
             if (ms > g.last_batch_ms) g.last_batch_ms = ms;
         }
 #endif
-        copy_d2h(&bad, t->flag.p, 4, g.main);
+#ifndef MB200_EMU
+        for (auto& e : t->ev_v)
+            if (e) MB_CUDA(cudaEventSynchronize(e));
+#endif
+        copy_d2h(&bad, t->flag, 4, g.main);
         stream_sync(g.main);
         if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
         memcpy(t->out, t->staged, t->n_proofs * 192);
@@ -361,6 +431,7 @@ int mb200_init(const int* device_ids, int n_devices) {
     if (prop.major < 10) fail(MB200_ECUDA, "device %s is not sm_100 (compute capability %ld.x)", prop.name, (long)prop.major);
     g.device = dev;
     MB_CUDA(cudaStreamCreateWithFlags(&g.main, cudaStreamNonBlocking));
+    for (auto& v : g.vstream) MB_CUDA(cudaStreamCreateWithFlags(&v, cudaStreamNonBlocking));
 #else
     (void)device_ids;
     (void)n_devices;
@@ -377,9 +448,15 @@ int mb200_shutdown(void) {
     for (auto& kv : g.ntt) delete kv.second;
     g.ntt.clear();
     set_ctx_count(0);
+    for (auto* r : g_res_free) delete r;
+    g_res_free.clear();
     g.msm = MsmScratch();
 #ifndef MB200_EMU
     cudaStreamDestroy(g.main);
+    for (auto& v : g.vstream) {
+        cudaStreamSynchronize(v);
+        cudaStreamDestroy(v);
+    }
 #endif
     g.inited = false;
     MB_API_END

@@ -381,7 +381,6 @@ struct ProveCtx {  // one in-flight chunk: its streams and scratch
     cudaStream_t tail[4] = {0, 0, 0, 0};  // high priority: reduction tails of A, B1, B2; [3] = H+L tail, assembly
     bool split_tail = false;
     DevBuf abc, w0, w1, w2, w3, pool, flag, res_hl, res_a, res_b1, res_b2, cmul, proofs;
-    DevBuf aff_a, aff_b, aff_c, ok;  // self-check: affine proof points, per-proof verdict
     MsmScratch msm, msm_side[3];
     bool have_stream = false;
 #ifndef MB200_EMU
@@ -409,9 +408,21 @@ inline void copy_rows(void* dst, size_t dpitch, const void* src, size_t spitch, 
 
 // Enqueue one chunk of proofs [first, first + count) on ctx.stream.  proofs_out:
 // host memory, 192 bytes per proof.  No host synchronisation.
-// verify_out: pinned host array of per-proof verdicts, or nullptr to skip the self-check.
+// Where a batch's self-check lives: per-batch device buffers (so the chunk context is free again
+// as soon as the proofs are encoded) and the stream the check runs on.
+struct VerifySink {
+    G1Affine* a = nullptr;   // [n_proofs] affine proof points
+    G2Affine* b = nullptr;
+    G1Affine* c = nullptr;
+    uint32_t* inputs = nullptr;  // [n_proofs][n_inputs] scalars
+    uint32_t* ok_dev = nullptr;  // [n_proofs]
+    uint32_t* ok_host = nullptr; // pinned
+    cudaStream_t stream = 0;     // latency-bound verifier kernels run here, next to the following chunks
+    bool on() const { return a != nullptr; }
+};
+
 inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, size_t first, uint32_t count,
-                        size_t rows, uint8_t* proofs_out, uint32_t* verify_out = nullptr) {
+                        size_t rows, uint8_t* proofs_out, const VerifySink& vs = VerifySink()) {
     cudaStream_t s = x.stream;
     const uint32_t m = P.m;
     size_t polys = (size_t)count * 3;
@@ -505,36 +516,42 @@ inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, siz
     launch_proof_cmul(ca, s);
     FinishArgs fa{(size_t)count * 3, x.res_a.as<G1XYZZ>(), x.res_b2.as<G2XYZZ>(), x.res_hl.as<G1XYZZ>(),
                   x.cmul.as<G1XYZZ>(), x.proofs.as<uint8_t>(), nullptr, nullptr, nullptr};
-    if (verify_out) {
-        x.aff_a.ensure(count * sizeof(G1Affine));
-        x.aff_b.ensure(count * sizeof(G2Affine));
-        x.aff_c.ensure(count * sizeof(G1Affine));
-        x.ok.ensure((size_t)count * 4);
-        fa.aff_a = x.aff_a.as<G1Affine>();
-        fa.aff_b = x.aff_b.as<G2Affine>();
-        fa.aff_c = x.aff_c.as<G1Affine>();
+    if (vs.on()) {
+        fa.aff_a = vs.a + first;
+        fa.aff_b = vs.b + first;
+        fa.aff_c = vs.c + first;
     }
     launch_proof_finish(fa, s);
     copy_d2h(proofs_out + first * 192, x.proofs.p, (size_t)count * 192, s);
-    if (verify_out) {
-        // verify_proof(vk, proof, inputs) as at masp_proofs/src/sapling/prover.rs:148, :266
+    if (vs.on()) {
+        // verify_proof(vk, proof, inputs) as at masp_proofs/src/sapling/prover.rs:148, :266.  The
+        // public inputs are copied out of the chunk's scalar pool so that nothing the check reads
+        // belongs to the chunk context any more.
+        uint32_t* vin = vs.inputs + first * (size_t)P.n_inputs * 8;
+        copy_rows(vin, (size_t)P.n_inputs * 32, x.pool.as<uint8_t>() + P.idx_inputs * 32, P.pool_stride * 32,
+                  (size_t)P.n_inputs * 32, count, true, s);
+        cudaStream_t v = vs.stream;
+#ifndef MB200_EMU
+        MB_CUDA(cudaEventRecord(x.ev_tail, s));
+        MB_CUDA(cudaStreamWaitEvent(v, x.ev_tail, 0));
+#endif
         VerifyArgs va;
         va.nthreads = count;
         va.pa = fa.aff_a;
         va.pb = fa.aff_b;
         va.pc = fa.aff_c;
-        va.inputs = x.pool.as<uint32_t>() + P.idx_inputs * 8;
-        va.input_stride = P.pool_stride;
+        va.inputs = vin;
+        va.input_stride = P.n_inputs;
         va.n_inputs = P.n_inputs;
         va.vk = {P.vk_ic.as<G1Affine>(), P.vk_g2.as<G2Affine>() + 1, P.vk_g2.as<G2Affine>() + 2, P.vk_ab.as<Fp12>()};
-        va.ok = x.ok.as<uint32_t>();
-        launch_verify_proofs(va, s);
-        copy_d2h(verify_out + first, x.ok.p, (size_t)count * 4, s);
+        va.ok = vs.ok_dev + first;
+        launch_verify_proofs(va, v);
+        copy_d2h(vs.ok_host + first, va.ok, (size_t)count * 4, v);
     }
 #ifndef MB200_EMU
     if (x.split_tail) {  // the chunk is done when its tail is: later work on this context queues behind it
-        MB_CUDA(cudaEventRecord(x.ev_tail, s));
-        MB_CUDA(cudaStreamWaitEvent(x.stream, x.ev_tail, 0));
+        MB_CUDA(cudaEventRecord(x.ev_acc[3], s));
+        MB_CUDA(cudaStreamWaitEvent(x.stream, x.ev_acc[3], 0));
     }
 #endif
 }
