@@ -198,10 +198,45 @@ def circuit_path(pv, key, shape, n, rounds, seed=20261017, torch=None):
         done += n
     th.join()
     t_pipe = time.perf_counter() - t0
+
+    def pipelined():
+        """One more pipelined pass (used for the variant with the self-check on)."""
+        qq, fr = queue.Queue(maxsize=1), queue.Queue()
+        for b in ring:
+            fr.put(b)
+
+        def prod():
+            for k in range(rounds):
+                qq.put(circ.synthesize(packed[k], out=fr.get()))
+        t1 = time.perf_counter()
+        thr = threading.Thread(target=prod)
+        thr.start()
+        tk, kp = [], []
+        for k in range(rounds):
+            i_k, a_k = qq.get()
+            kp.append((i_k, a_k))
+            tk.append(pv.prove_submit_witness(params, n, i_k, a_k, r_b, s_b, outs[k]))
+            if len(tk) > 2:
+                pv.prove_wait(tk.pop(0))
+                fr.put(kp.pop(0))
+        while tk:
+            pv.prove_wait(tk.pop(0))
+            fr.put(kp.pop(0))
+        thr.join()
+        return rounds * n / (time.perf_counter() - t1)
+    # the reference's spend_proof also runs verify_proof on the fresh proof (sapling/prover.rs:148):
+    # same pipeline with the device self-check on (audit mode: this key is not a valid CRS, so the
+    # verdicts are 'fail' by construction; the kernel and its cost are the same)
+    pv.set_option("verify", 2)
+    try:
+        with_check = pipelined()
+    finally:
+        pv.set_option("verify", 0)
     return {
         "what": "real Spend witnesses through mb200_circuit_synthesize + mb200_prove_batch_witness "
                 "(what TxProver::spend_proof does per description, batched)",
-        "proofs_per_s_pipelined": done / t_pipe, "batch": n, "rounds": rounds,
+        "proofs_per_s_pipelined": done / t_pipe, "proofs_per_s_pipelined_with_self_check": with_check,
+        "batch": n, "rounds": rounds,
         "host_witness_per_s": n / t_synth, "host_threads": os.cpu_count(),
         "device_proofs_per_s": n / t_prove,
         "h2d_bytes_per_proof": 32 * (circ.n_aux + circ.n_inputs + 2),
