@@ -373,6 +373,18 @@ static void r1cs_upload(R1csDev& R, const mb200_circuit& c, size_t idx_aux, size
         copy_h2d(R.cidx[k].p, cidx.data(), cidx.size() * 4, g.main);
         stream_sync(g.main);  // the staging vectors die at the end of this iteration
     }
+    {  // rows by descending total non-zero count (stable: equal rows stay in constraint order)
+        std::vector<uint32_t> order(c.n_constraints);
+        for (uint32_t i = 0; i < c.n_constraints; ++i) order[i] = i;
+        auto cost = [&](uint32_t r) {
+            return (c.A.rowptr[r + 1] - c.A.rowptr[r]) + (c.B.rowptr[r + 1] - c.B.rowptr[r]) +
+                   (c.C.rowptr[r + 1] - c.C.rowptr[r]);
+        };
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cost(x) > cost(y); });
+        R.order.alloc(order.size() * 4 + 4);
+        copy_h2d(R.order.p, order.data(), order.size() * 4, g.main);
+        stream_sync(g.main);
+    }
     // mbh::Fr (4 x u64 Montgomery, R = 2^256) has the same memory image as the device Fr (8 x u32)
     R.dict.alloc(dict_vals.size() * 32);
     copy_h2d(R.dict.p, dict_vals.data(), dict_vals.size() * 32, g.main);
@@ -607,6 +619,7 @@ int mb200_circuit_rows(const mb200_circuit* c, size_t n, const uint8_t* inputs, 
     ra.pool_stride = stride;
     ra.idx_inputs = c->n_aux;
     ra.abc = abc.as<Fr>();
+    ra.order = R.order.as<uint32_t>();
     launch_r1cs_eval(ra, g.main);
     uint32_t bad = 0;
     copy_d2h(&bad, flag.p, 4, g.main);

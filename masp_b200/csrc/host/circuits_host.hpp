@@ -111,34 +111,29 @@ struct Jubjub {
         ext_to_affine(e.data(), sums, n);
     }
     // Montgomery chain S_0 = T_0, S_k = T_k + S_(k-1): the slopes lam[k] (k >= 1) of each step.
+    // The running sum is kept projective, (X : Y : Z); a step's slope is u / v with
+    // u = ty Z - Y, v = tx Z - X, so only the v's have to be inverted, all together.
     // Returns false if a step is exceptional (equal x: the reference's DivisionByZero).
     bool montgomery_chain_slopes(const Fr* tx, const Fr* ty, size_t n, Fr* lam) const {
         if (n < 2) return true;
-        std::vector<Fr> X(n), Y(n), Z(n), scratch;
-        X[0] = tx[0];
-        Y[0] = ty[0];
-        Z[0] = Fr::one();
+        std::vector<Fr> u(n), v(n), scratch;
+        Fr X = tx[0], Y = ty[0], Z = Fr::one();
+        v[0] = Fr::one();
         for (size_t k = 1; k < n; ++k) {  // projective chord: (X:Y:Z) + affine (tx, ty)
-            const Fr &X1 = X[k - 1], &Y1 = Y[k - 1], &Z1 = Z[k - 1];
-            Fr x2z = tx[k] * Z1;
-            Fr u = ty[k] * Z1 - Y1, v = x2z - X1;
-            Fr vv = v.square(), vvv = vv * v;
-            Fr W = u.square() * Z1 - vv * (mont_a * Z1 + x2z + X1);
-            X[k] = W * v;
-            Y[k] = u * (X1 * vv - W) - Y1 * vvv;
-            Z[k] = vvv * Z1;
+            Fr x2z = tx[k] * Z;
+            Fr uu = ty[k] * Z - Y, vv1 = x2z - X;
+            u[k] = uu;
+            v[k] = vv1;
+            if (k + 1 == n) break;  // the last sum itself is not needed
+            Fr vv = vv1.square(), vvv = vv * vv1;
+            Fr W = uu.square() * Z - vv * (mont_a * Z + x2z + X);
+            Fr Xn = W * vv1;
+            Y = uu * (X * vv - W) - Y * vvv;
+            X = Xn;
+            Z = vvv * Z;
         }
-        bool bad = batch_inverse(Z.data(), n, scratch);
-        // affine partial sums, then all slope denominators at once
-        std::vector<Fr> sx(n), sy(n), dx(n);
-        for (size_t k = 0; k < n; ++k) {
-            sx[k] = X[k] * Z[k];
-            sy[k] = Y[k] * Z[k];
-        }
-        dx[0] = Fr::one();
-        for (size_t k = 1; k < n; ++k) dx[k] = sx[k - 1] - tx[k];
-        bad |= batch_inverse(dx.data(), n, scratch);
-        for (size_t k = 1; k < n; ++k) lam[k] = (sy[k - 1] - ty[k]) * dx[k];
+        bool bad = batch_inverse(v.data(), n, scratch);
+        for (size_t k = 1; k < n; ++k) lam[k] = u[k] * v[k];
         return !bad;
     }
 

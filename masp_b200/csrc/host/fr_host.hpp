@@ -124,6 +124,17 @@ struct Fr {
         memcpy(out, t.v, 32);
     }
     void to_bytes(uint8_t out[32]) const {
+        // most witness values are booleans: 0 and 1 need no Montgomery reduction
+        if (is_zero()) {
+            memset(out, 0, 32);
+            return;
+        }
+        if (v[0] == 0x00000001fffffffeull && v[1] == 0x5884b7fa00034802ull && v[2] == 0x998c4fefecbc4ff5ull &&
+            v[3] == 0x1824b159acc5056full) {
+            memset(out, 0, 32);
+            out[0] = 1;
+            return;
+        }
         uint64_t w[4];
         to_words(w);
         memcpy(out, w, 32);  // little-endian host

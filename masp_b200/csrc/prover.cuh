@@ -473,6 +473,7 @@ inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, siz
         ra.pool_stride = P.pool_stride;
         ra.idx_inputs = P.idx_inputs;
         ra.abc = x.abc.as<Fr>();
+        ra.order = R.order.as<uint32_t>();
         launch_r1cs_eval(ra, s);
     }
 

@@ -27,10 +27,13 @@ struct R1csArgs {
     const Fr* pool;
     size_t pool_stride, idx_inputs;
     Fr* abc;                  // [proof][3][rows]
+    const uint32_t* order;    // constraint rows by descending non-zero count: the 32 lanes of a warp
+                              // get rows of similar length (a few rows have ~255 terms, most have 1-3)
 };
 MB_HD void r1cs_eval_body(const R1csArgs& a, size_t tid) {
     size_t proof = tid / a.rows;
     uint32_t row = (uint32_t)(tid - proof * a.rows);
+    if (row < a.ncons) row = a.order[row];
     const Fr* z = a.pool + proof * a.pool_stride;
     Fr* out = a.abc + proof * 3 * (size_t)a.rows + row;
     if (row >= a.ncons) {  // bellman appends one row per input: a = input, b = c = 0
@@ -57,7 +60,7 @@ MB_HD void r1cs_eval_body(const R1csArgs& a, size_t tid) {
 MB_K_NTT(r1cs_eval, R1csArgs, r1cs_eval_body, 128)
 
 struct R1csDev {
-    DevBuf rowptr[3], col[3], cidx[3], dict;
+    DevBuf rowptr[3], col[3], cidx[3], dict, order;
     uint32_t ncons = 0, n_inputs = 0, n_aux = 0;
     bool bound = false;
 };
