@@ -113,7 +113,13 @@ MB_HD void ntt2_body(const NttArgs& a, size_t tid) { ntt_body<2>(a, tid); }
 MB_HD void ntt3_body(const NttArgs& a, size_t tid) { ntt_body<3>(a, tid); }
 MB_K_NTT(ntt_pass_r2, NttArgs, ntt1_body, 128)
 MB_K_NTT(ntt_pass_r4, NttArgs, ntt2_body, 128)
+// The radix-8 pass is latency-bound on its own (152 registers, 12 warps per SM, 45 % of the
+// multiplier: profiles/r01_ncu_ntt_pass_r8.md), but inside the prover that does not show:
+// register-capped variants for 4 / 5 / 6 resident blocks (profiles/r01_ntt_occupancy_sweep.jsonl)
+// and "thin" launches that leave room for accumulation blocks (r01_ntt_thin_sweep.jsonl) were
+// measured at +-0.3 % and -4...-8 % of the proof rate, so the plain kernel stays.
 MB_K_NTT(ntt_pass_r8, NttArgs, ntt3_body, 128)
+inline void launch_ntt_r8(const NttArgs& a, cudaStream_t s) { launch_ntt_pass_r8(a, s); }
 
 // ---------------------------------------------------------------------------
 // domain tables
@@ -246,7 +252,7 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
         a.srcc = first ? p.srcc : nullptr;
         a.k1 = d.k1;
         a.k2 = d.k2;
-        if (K == 3) launch_ntt_pass_r8(a, s);
+        if (K == 3) launch_ntt_r8(a, s);
         else if (K == 2) launch_ntt_pass_r4(a, s);
         else launch_ntt_pass_r2(a, s);
         cur = a.dst;

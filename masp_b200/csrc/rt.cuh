@@ -77,6 +77,18 @@ extern unsigned long long g_launches;  // kernels launched by this library (benc
         MB_CUDA(cudaGetLastError());                                                     \
         ::mb::g_launches++;                                                              \
     }
+// same, with a minimum number of resident blocks per SM (caps the registers per thread)
+#define MB_KERNEL_DEF_OCC(name, Args, body, BLOCK, MINB)                                 \
+    __global__ void __launch_bounds__(BLOCK, MINB) name(const Args a) {                  \
+        size_t tid = (size_t)blockIdx.x * BLOCK + threadIdx.x;                           \
+        if (tid < a.nthreads) body(a, tid);                                              \
+    }                                                                                    \
+    void launch_##name(const Args& a, cudaStream_t s) {                                  \
+        if (!a.nthreads) return;                                                         \
+        name<<<(unsigned)((a.nthreads + BLOCK - 1) / BLOCK), BLOCK, 0, s>>>(a);          \
+        MB_CUDA(cudaGetLastError());                                                     \
+        ::mb::g_launches++;                                                              \
+    }
 template <class T>
 __host__ __device__ __forceinline__ T mb_atomic_add(T* p, T v) {
 #ifdef __CUDA_ARCH__
@@ -127,6 +139,7 @@ inline void stream_sync(cudaStream_t s) { MB_CUDA(cudaStreamSynchronize(s)); }
         for (size_t tid = 0; tid < a.nthreads; ++tid) body(a, tid);                      \
         ::mb::g_launches++;                                                              \
     }
+#define MB_KERNEL_DEF_OCC(name, Args, body, BLOCK, MINB) MB_KERNEL_DEF(name, Args, body, BLOCK)
 template <class T>
 inline T emu_atomic_add(T* p, T v) {
     T o = *p;

@@ -86,6 +86,40 @@ def test_witness_matches_oracle(kind, depth):
     assert {col[e]: val[e] for e in range(rp[row], rp[row + 1])} == want
 
 
+@pytest.mark.parametrize("value,rights", [(0, 0b00), (2 ** 64 - 1, 0b11), (1, 0b01)])
+def test_edge_values_match_oracle(value, rights):
+    """Extremes the reference's own circuit tests walk (value 0 / u64::MAX, every
+    position bit pattern: circuit/sapling.rs:640-700 loops over tree positions)."""
+    depth = 2
+    c = C.Circuit(C.CONVERT, depth)
+    path = [(RND.randrange(R), bool((rights >> i) & 1)) for i in range(depth)]
+    rcv = mc.JUBJUB_ORDER - 1  # largest scalar
+    anchor = mc.convert_native_anchor(AG, path)
+    cs = ConstraintSystem()
+    mc.convert_circuit(cs, AG, value, rcv, path, anchor)
+    assert cs.is_satisfied()
+    inst = C.Convert(C.ValueCommitmentOpening(AG, value, rcv), path, anchor)
+    assert c.root(inst) == anchor
+    inputs, aux = c.synthesize([inst])
+    assert inputs == ib(cs.inputs) and aux == ib(cs.aux)
+    if value == 0:
+        # value 0: the anchor check `(cur - rt) * value = 0` holds for ANY anchor (convert.rs:113-121)
+        free = C.Convert(C.ValueCommitmentOpening(AG, 0, rcv), path, (anchor + 5) % R)
+        i2, a2 = c.synthesize([free])
+        cs2 = ConstraintSystem()
+        mc.convert_circuit(cs2, AG, 0, rcv, path, (anchor + 5) % R)
+        assert cs2.is_satisfied() and i2 == ib(cs2.inputs) and a2 == ib(cs2.aux)
+
+
+def test_empty_batch_and_threads():
+    c = C.Circuit(C.OUTPUT)
+    assert c.synthesize([]) == (b"", b"")
+    inst, cs = make_instance(C.OUTPUT, 0)
+    one = c.synthesize([inst], threads=1)
+    many = c.synthesize([inst] * 5, threads=3)
+    assert many[0] == one[0] * 5 and many[1] == one[1] * 5
+
+
 def test_bad_witnesses_are_rejected():
     c = C.Circuit(C.CONVERT, 1)
     inst, _ = make_instance(C.CONVERT, 1)
