@@ -280,6 +280,8 @@ MB_HD void acc_body(const AccArgs<F>& a, size_t tid) {
 MB_HD void acc_g1_body(const AccArgs<Fp>& a, size_t tid) { acc_body<Fp>(a, tid); }
 MB_HD void acc_g2_body(const AccArgs<Fp2>& a, size_t tid) { acc_body<Fp2>(a, tid); }
 MB_K_MSM_G1(msm_accumulate_g1, AccArgs<Fp>, acc_g1_body, 128)
+// (capped at 128 registers for a fourth resident block it spills ~470 bytes and is 1 % slower:
+// profiles/r01_acc_128reg_ab.jsonl)
 MB_K_MSM_G2(msm_accumulate_g2, AccArgs<Fp2>, acc_g2_body, 64)
 
 // bucket sum = sum of its segments' partial sums (one for almost every bucket)
