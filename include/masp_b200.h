@@ -176,6 +176,11 @@ int mb200_prove_batch_witness(const mb200_params* p, size_t n_proofs, const uint
  *     e(A,B) = e(alpha,beta) e(sum x_i IC_i, gamma) e(C, delta). */
 int mb200_verify_batch(const mb200_params* p, size_t n, const uint8_t* proofs_uncompressed, const uint8_t* inputs,
                        uint8_t* ok_out);
+/* The same for proofs as they travel: n x 192 bytes (Proof::write: A, B, C compressed).  Reading
+ * them is bellman's Proof::read -- each point must decompress to a curve point of the prime-order
+ * subgroup -- and a proof that does not read is simply not accepted (ok_out[i] = 0), as at the
+ * verifier's call sites masp_proofs/src/sapling/verifier/single.rs:60, 77, 93. */
+int mb200_verify_proofs(const mb200_params* p, size_t n, const uint8_t* proofs, const uint8_t* inputs, uint8_t* ok_out);
 
 /* multiexp over arbitrary bases (ec-gpu-gen `multiexp`, full density);
  * result uncompressed.  No table is precomputed on this path. */

@@ -680,6 +680,43 @@ int mb200_verify_batch(const mb200_params* p, size_t n, const uint8_t* proofs_un
     MB_API_END
 }
 
+int mb200_verify_proofs(const mb200_params* p, size_t n, const uint8_t* proofs, const uint8_t* inputs, uint8_t* ok_out) {
+    MB_API_BEGIN
+    require_init();
+    if (!p || !p->p || (n && (!proofs || !inputs || !ok_out))) fail(MB200_EINVAL, "null argument%s", "");
+    if (n == 0) return MB200_OK;
+    const Params& P = *p->p;
+    DevBuf raw(n * 192), pa(n * sizeof(G1Affine)), pb(n * sizeof(G2Affine)), pc(n * sizeof(G1Affine)), bad(n * 4),
+        flag(4), din(n * P.n_inputs * 32), ok(n * 4);
+    copy_h2d(raw.p, proofs, n * 192, g.main);
+    copy_h2d(din.p, inputs, n * P.n_inputs * 32, g.main);
+    dev_memset(bad.p, 0, n * 4, g.main);
+    dev_memset(flag.p, 0, 4, g.main);
+    ProofReadArgs ra{n * 3, raw.as<uint8_t>(), pa.as<G1Affine>(), pb.as<G2Affine>(), pc.as<G1Affine>(), bad.as<uint32_t>()};
+    launch_proof_read(ra, g.main);
+    check_scalars_dev(din.as<Fr>(), n * P.n_inputs, 0, 1, flag.as<uint32_t>(), g.main);
+    VerifyArgs va;
+    va.nthreads = n;
+    va.pa = pa.as<G1Affine>();
+    va.pb = pb.as<G2Affine>();
+    va.pc = pc.as<G1Affine>();
+    va.inputs = din.as<uint32_t>();
+    va.input_stride = P.n_inputs;
+    va.n_inputs = P.n_inputs;
+    va.vk = {P.vk_ic.as<G1Affine>(), P.vk_g2.as<G2Affine>() + 1, P.vk_g2.as<G2Affine>() + 2, P.vk_ab.as<Fp12>()};
+    va.ok = ok.as<uint32_t>();
+    launch_verify_proofs(va, g.main);
+    std::vector<uint32_t> hok(n), hbad(n);
+    uint32_t hflag = 0;
+    copy_d2h(hok.data(), ok.p, n * 4, g.main);
+    copy_d2h(hbad.data(), bad.p, n * 4, g.main);
+    copy_d2h(&hflag, flag.p, 4, g.main);
+    stream_sync(g.main);
+    if (hflag) fail(MB200_ESCALAR, "a public input is not canonical (>= r)%s", "");
+    for (size_t i = 0; i < n; ++i) ok_out[i] = (hok[i] && !hbad[i]) ? 1 : 0;
+    MB_API_END
+}
+
 int mb200_prove_batch_witness(const mb200_params* p, size_t n_proofs, const uint8_t* inputs, const uint8_t* aux,
                               const uint8_t* r, const uint8_t* s, uint8_t* proofs_out) {
     MB_API_BEGIN

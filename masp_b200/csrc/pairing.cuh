@@ -313,6 +313,156 @@ MB_HD void verify_body(const VerifyArgs& a, size_t tid) {
     a.ok[tid] = f12_is_one(final_exponentiation(f)) ? 1u : 0u;
 }
 
+// ---------------------------------------------------------------------------
+// compressed proof points (Proof::read: zkcrypto from_compressed, i.e. on-curve AND in the
+// prime-order subgroup), for verifying proofs that arrive as their 192 wire bytes
+// (masp_proofs/src/sapling/verifier/single.rs:60,77,93 read the zkproof this way)
+// ---------------------------------------------------------------------------
+MB_COLD Fp fp_pow_limbs(const Fp& a, const uint32_t* e, int nbits) {
+    Fp r = Fp::one();
+    MB_NOUNROLL
+    for (int i = nbits - 1; i >= 0; --i) {
+        r = Fp::sqr(r);
+        if ((e[i >> 5] >> (i & 31)) & 1) r = Fp::mul(r, a);
+    }
+    return r;
+}
+MB_COLD Fp2 fp2_pow_limbs(const Fp2& a, const uint32_t* e, int nbits) {
+    Fp2 r = Fp2::one();
+    MB_NOUNROLL
+    for (int i = nbits - 1; i >= 0; --i) {
+        r = f2_sqr(r);
+        if ((e[i >> 5] >> (i & 31)) & 1) r = f2_mul(r, a);
+    }
+    return r;
+}
+// (p + k) >> s as limbs, for the small k, s the square roots need
+MB_HD void p_shifted(int add, int sub, int shift, uint32_t out[12]) {
+    uint32_t t[12];
+    uint64_t c = (uint64_t)add;
+    for (int i = 0; i < 12; ++i) {
+        c += FpCfg::mod(i);
+        t[i] = (uint32_t)c;
+        c >>= 32;
+    }
+    uint64_t b = (uint64_t)sub;
+    for (int i = 0; i < 12; ++i) {
+        uint64_t d = (uint64_t)t[i] - b;
+        t[i] = (uint32_t)d;
+        b = (d >> 63) & 1;
+    }
+    for (int i = 0; i < 12; ++i) out[i] = (t[i] >> shift) | (shift && i + 1 < 12 ? t[i + 1] << (32 - shift) : 0);
+}
+// p = 3 mod 4: sqrt(a) = a^((p+1)/4) when a is a square
+MB_COLD bool fp_sqrt(const Fp& a, Fp& out) {
+    uint32_t e[12];
+    p_shifted(1, 0, 2, e);
+    out = fp_pow_limbs(a, e, 384);
+    return Fp::sqr(out).eq(a);
+}
+// Fp2 = Fp[u]/(u^2+1), p = 3 mod 4 (Adj & Rodriguez-Henriquez, Algorithm 9)
+MB_COLD bool fp2_sqrt(const Fp2& a, Fp2& out) {
+    if (a.is_zero()) {
+        out = Fp2::zero();
+        return true;
+    }
+    uint32_t e[12];
+    p_shifted(0, 3, 2, e);                      // (p - 3) / 4
+    Fp2 a1 = fp2_pow_limbs(a, e, 384);
+    Fp2 alpha = f2_mul(f2_sqr(a1), a);          // a^((p-1)/2)
+    Fp2 x0 = f2_mul(a1, a);
+    Fp2 minus_one = Fp2::neg(Fp2::one());
+    Fp2 a0 = f2_mul(f2_conj(alpha), alpha);     // alpha^(p+1)
+    if (a0.eq(minus_one)) return false;
+    if (alpha.eq(minus_one)) {
+        out = {Fp::neg(x0.c1), x0.c0};          // u * x0
+    } else {
+        p_shifted(0, 1, 1, e);                  // (p - 1) / 2
+        Fp2 b = fp2_pow_limbs(Fp2::add(Fp2::one(), alpha), e, 384);
+        out = f2_mul(b, x0);
+    }
+    return f2_sqr(out).eq(a);
+}
+MB_HD void fr_modulus_words(uint32_t r[8]) {
+    for (int i = 0; i < 8; ++i) r[i] = FrCfg::mod(i);
+}
+// false: malformed, not on the curve, or outside the prime-order subgroup
+MB_COLD bool g1_decode_compressed(const uint8_t* b, G1Affine& out) {
+    if (!(b[0] & 0x80)) return false;
+    if (b[0] & 0x40) {
+        uint32_t o = b[0] & 0x3f & ~0x40u;
+        for (int i = 1; i < 48; ++i) o |= b[i];
+        out = G1Affine::inf();
+        return o == 0;
+    }
+    uint8_t t[48];
+    for (int i = 0; i < 48; ++i) t[i] = b[i];
+    t[0] &= 0x1f;
+    Fp x;
+    fp_limbs_from_be(t, x);
+    if (Fp::std_ge_mod(x)) return false;
+    out.x = Fp::from_std(x);
+    Fp four = Fp::dbl(Fp::dbl(Fp::one()));
+    Fp y;
+    if (!fp_sqrt(Fp::add(Fp::mul(Fp::sqr(out.x), out.x), four), y)) return false;
+    bool larger = Fp::std_gt_half(Fp::to_std(y));
+    if (larger != ((b[0] & 0x20) != 0)) y = Fp::neg(y);
+    out.y = y;
+    uint32_t r[8];
+    fr_modulus_words(r);
+    return xyzz_mul(G1XYZZ::from_affine(out), r).is_inf();
+}
+MB_COLD bool g2_decode_compressed(const uint8_t* b, G2Affine& out) {
+    if (!(b[0] & 0x80)) return false;
+    if (b[0] & 0x40) {
+        uint32_t o = b[0] & 0x3f & ~0x40u;
+        for (int i = 1; i < 96; ++i) o |= b[i];
+        out = G2Affine::inf();
+        return o == 0;
+    }
+    uint8_t t[48];
+    for (int i = 0; i < 48; ++i) t[i] = b[i];
+    t[0] &= 0x1f;
+    Fp c1, c0;
+    fp_limbs_from_be(t, c1);
+    fp_limbs_from_be(b + 48, c0);
+    if (Fp::std_ge_mod(c1) || Fp::std_ge_mod(c0)) return false;
+    out.x = {Fp::from_std(c0), Fp::from_std(c1)};
+    Fp four = Fp::dbl(Fp::dbl(Fp::one()));
+    Fp2 bb = {four, four};  // 4 (1 + u)
+    Fp2 y;
+    if (!fp2_sqrt(Fp2::add(f2_mul(f2_sqr(out.x), out.x), bb), y)) return false;
+    bool larger = y.c1.is_zero() ? Fp::std_gt_half(Fp::to_std(y.c0)) : Fp::std_gt_half(Fp::to_std(y.c1));
+    if (larger != ((b[0] & 0x20) != 0)) y = Fp2::neg(y);
+    out.y = y;
+    uint32_t r[8];
+    fr_modulus_words(r);
+    return xyzz_mul(G2XYZZ::from_affine(out), r).is_inf();
+}
+struct ProofReadArgs {
+    size_t nthreads;  // 3 * proofs
+    const uint8_t* proofs;  // 192 bytes each: A (48) | B (96) | C (48), compressed
+    G1Affine* pa;
+    G2Affine* pb;
+    G1Affine* pc;
+    uint32_t* bad;  // per proof: set when any of its points is rejected
+};
+MB_HD void proof_read_body(const ProofReadArgs& a, size_t tid) {
+    size_t proof = tid / 3;
+    uint32_t which = (uint32_t)(tid - proof * 3);
+    const uint8_t* p = a.proofs + 192 * proof;
+    bool ok;
+    if (which == 0) ok = g1_decode_compressed(p, a.pa[proof]);
+    else if (which == 1) ok = g2_decode_compressed(p + 48, a.pb[proof]);
+    else ok = g1_decode_compressed(p + 144, a.pc[proof]);
+    if (!ok) {
+        if (which == 0) a.pa[proof] = G1Affine::inf();
+        else if (which == 1) a.pb[proof] = G2Affine::inf();
+        else a.pc[proof] = G1Affine::inf();
+        a.bad[proof] = 1;
+    }
+}
+
 // self-test: the x-chain against the plain power, Frobenius maps against plain powers' structure
 struct PairSelfTestArgs {
     size_t nthreads;  // 1
@@ -346,10 +496,12 @@ MB_HD void pair_selftest_body(const PairSelfTestArgs& a, size_t) {
 
 #ifdef MB_DEFINE_PAIR
 MB_KERNEL_DEF(pair_selftest, PairSelfTestArgs, pair_selftest_body, 32)
+MB_KERNEL_DEF(proof_read, ProofReadArgs, proof_read_body, 32)
 MB_KERNEL_DEF(pair_prep, PairPrepArgs, pair_prep_body, 32)
 MB_KERNEL_DEF(verify_proofs, VerifyArgs, verify_body, 32)
 #else
 MB_KERNEL_DECL(pair_selftest, PairSelfTestArgs)
+MB_KERNEL_DECL(proof_read, ProofReadArgs)
 MB_KERNEL_DECL(pair_prep, PairPrepArgs)
 MB_KERNEL_DECL(verify_proofs, VerifyArgs)
 #endif

@@ -241,6 +241,25 @@ def verify_batch(params, proofs_uncompressed, public_inputs):
     return [b != 0 for b in ok.raw]
 
 
+def verify_proofs(params, proofs, public_inputs):
+    """groth16::verify_proof for proofs in wire form (192 bytes each, Proof::read applied on the
+    device: decompression + subgroup checks).  public_inputs as for verify_batch.  A proof that
+    does not even read is reported False, like any other invalid proof."""
+    _ensure_init()
+    n = len(proofs)
+    if n == 0:
+        return []
+    if any(len(p) != GROTH_PROOF_SIZE for p in proofs):
+        raise ValueError("a proof is %d bytes" % GROTH_PROOF_SIZE)
+    inp = b"".join((1).to_bytes(32, "little") + b"".join(int(x).to_bytes(32, "little") for x in xs)
+                   for xs in public_inputs)
+    if len(inp) != 32 * n * params.n_inputs:
+        raise ValueError("public input count does not match the verifying key")
+    ok = ctypes.create_string_buffer(n)
+    check(_lib.lib().mb200_verify_proofs(params._h, n, _ptr(b"".join(proofs)), _ptr(inp), ctypes.cast(ok, ctypes.c_void_p)))
+    return [b != 0 for b in ok.raw]
+
+
 def create_proof(assignment, params, r, s):
     """bellman create_proof(circuit, params, r, s) after synthesis -> 192 bytes."""
     return create_proof_batch([assignment], params, [r], [s])[0]

@@ -53,6 +53,16 @@ def _check(pv):
         assert e.value.code == -8
     finally:
         pv.set_option("verify", 0)
+    # proofs in wire form: Proof::read (decompression, subgroup checks) happens on the device
+    flipped = bytearray(proof)
+    flipped[0] ^= 0x20                          # the other square root for A: a valid point, wrong proof
+    off_curve = bytearray(proof)
+    off_curve[47] ^= 0x01                       # x of A changed: almost surely no point / not in the subgroup
+    no_flag = bytes([proof[0] & 0x7F]) + proof[1:]   # compression flag cleared: does not read
+    inf_a = bytes([0xC0]) + bytes(47) + proof[48:]   # A = identity: reads, cannot verify
+    got = pv.verify_proofs(P, [proof, bytes(flipped), bytes(off_curve), no_flag, inf_a, proof],
+                           [inputs[1:]] * 5 + [wrong])
+    assert got == [True, False, False, False, False, False]
     # malformed proof encodings are an error, not a verdict
     with pytest.raises(pv.Mb200Error):
         pv.verify_batch(P, [b"\xff" * 384], [inputs[1:]])
