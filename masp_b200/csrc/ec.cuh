@@ -195,6 +195,78 @@ MB_COLD XYZZ<F> xyzz_mul_affine(const Affine<F>& p, const uint32_t* k) {
     return acc;
 }
 
+// k * P on G1 with the GLV endomorphism phi(x, y) = (beta x, y) = lambda P, lambda = x^2 - 1
+// (lambda^2 + lambda + 1 = 0 mod r, 128 bits): k = k1 + k2 lambda by plain Euclidean division
+// (lambda is about sqrt(r), so both halves are below 2^128 without any lattice step), then
+// k1 P + k2 phi(P) with shared doublings: 128 doublings + at most 64 additions instead of
+// 256 + 64.  Used for the two scalar multiplications of the proof's C element (s A + r B1),
+// which sit on the latency path of every proof.
+MB_HD Fp glv_beta() {
+    constexpr uint32_t t[12] = {0x8671f071u, 0xcd03c9e4u, 0x1fcda5d2u, 0x5dab2246u, 0xd3851b95u, 0x587042afu,
+                                0x01bacb9eu, 0x8eb60ebeu, 0x83d050d2u, 0x03f97d6eu, 0x54638741u, 0x18f02065u};
+    Fp r;
+    for (int i = 0; i < 12; ++i) r.v[i] = t[i];
+    return r;
+}
+// k (8 words, < 2^256) = q * lambda + rem, lambda = 0xac45a4010001a40200000000ffffffff
+MB_HD void glv_split(const uint32_t* k, uint32_t rem[4], uint32_t q[4]) {
+    const uint32_t lam[4] = {0xffffffffu, 0x00000000u, 0x0001a402u, 0xac45a401u};
+    uint32_t r[5] = {0, 0, 0, 0, 0};  // running remainder, < 2 lambda < 2^129
+    uint32_t qq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    MB_NOUNROLL
+    for (int i = 255; i >= 0; --i) {
+        // r = (r << 1) | bit
+        r[4] = (r[4] << 1) | (r[3] >> 31);
+        r[3] = (r[3] << 1) | (r[2] >> 31);
+        r[2] = (r[2] << 1) | (r[1] >> 31);
+        r[1] = (r[1] << 1) | (r[0] >> 31);
+        r[0] = (r[0] << 1) | ((k[i >> 5] >> (i & 31)) & 1u);
+        // if r >= lambda: r -= lambda, quotient bit = 1
+        uint32_t d[5];
+        uint64_t br = 0;
+        for (int j = 0; j < 5; ++j) {
+            uint64_t x = (uint64_t)r[j] - (j < 4 ? lam[j] : 0u) - br;
+            d[j] = (uint32_t)x;
+            br = (x >> 63) & 1;
+        }
+        if (!br) {
+            for (int j = 0; j < 5; ++j) r[j] = d[j];
+            qq[i >> 5] |= 1u << (i & 31);
+        }
+    }
+    for (int j = 0; j < 4; ++j) {
+        rem[j] = r[j];
+        q[j] = qq[j];  // k < r < lambda^2 + ..., so the quotient fits 128 bits (checked by the caller's tests)
+    }
+}
+MB_COLD XYZZ<Fp> xyzz_mul_glv(const XYZZ<Fp>& p, const uint32_t* k) {
+    uint32_t k1[4], k2[4];
+    glv_split(k, k1, k2);
+    XYZZ<Fp> tab[16];
+    tab[0] = XYZZ<Fp>::inf();
+    tab[1] = p;
+    MB_NOUNROLL
+    for (int j = 2; j < 16; ++j) {
+        tab[j] = tab[j - 1];
+        xyzz_add_cold(tab[j], p);
+    }
+    const Fp beta = glv_beta();
+    XYZZ<Fp> acc = XYZZ<Fp>::inf();
+    MB_NOUNROLL
+    for (int w = 31; w >= 0; --w) {
+        MB_NOUNROLL
+        for (int d = 0; d < 4; ++d) acc = xyzz_dbl_cold(acc);
+        uint32_t d1 = (k1[w >> 3] >> ((w & 7) * 4)) & 15u, d2 = (k2[w >> 3] >> ((w & 7) * 4)) & 15u;
+        if (d1) xyzz_add_cold(acc, tab[d1]);
+        if (d2) {
+            XYZZ<Fp> t = tab[d2];
+            t.x = Fp::mul(t.x, beta);  // phi on XYZZ: x = X / ZZ
+            xyzz_add_cold(acc, t);
+        }
+    }
+    return acc;
+}
+
 typedef Affine<Fp> G1Affine;
 typedef Affine<Fp2> G2Affine;
 typedef XYZZ<Fp> G1XYZZ;

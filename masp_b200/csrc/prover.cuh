@@ -105,8 +105,8 @@ struct CmulArgs {
 MB_HD void cmul_body(const CmulArgs& a, size_t tid) {
     size_t proof = tid >> 1;
     const uint32_t* base = a.pool + proof * a.pool_stride * 8;
-    if (tid & 1) a.out[tid] = xyzz_mul(a.b1_res[proof], base + a.r_index * 8);
-    else a.out[tid] = xyzz_mul(a.a_res[proof], base + a.s_index * 8);
+    if (tid & 1) a.out[tid] = xyzz_mul_glv(a.b1_res[proof], base + a.r_index * 8);
+    else a.out[tid] = xyzz_mul_glv(a.a_res[proof], base + a.s_index * 8);
 }
 MB_K_G1(proof_cmul, CmulArgs, cmul_body, 32)
 

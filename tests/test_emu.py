@@ -127,3 +127,21 @@ def test_pair_rounds_variant():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu.py"), "-x", "-q", "-k",
                         "test_msm or test_prove_batch_chunked"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+@pytest.mark.slow
+def test_extreme_r_s(emu, oracle):
+    """r and s at the ends of the range: the GLV split of the two scalar multiplications in C
+    (k = k1 + k2 lambda, csrc/ec.cuh) must hold for 0, 1, lambda +- 1 and r - 1."""
+    sh = syn.micro_shape()
+    kb = oracle.params_from_logs(syn.key_logs(sh))
+    dens = sh.densities()
+    P = emu.Parameters.read(kb, dens)
+    w = syn.witness(sh, 0, oracle.fr_mul)
+    lam = 0xAC45A4010001A40200000000FFFFFFFF
+    ref = oracle.Params(kb, sh.n_aux, *dens)
+    for r_, s_ in ((0, 0), (1, syn.R_INT - 1), (syn.R_INT - 1, 1), (lam, lam - 1), (lam + 1, lam * lam % syn.R_INT),
+                   (1 << 254, (1 << 128) - 1)):
+        rb, sb = ib([r_]), ib([s_])
+        got = emu.create_proof(assignment(emu, w), P, rb, sb)
+        assert got == ref.prove(sh.rows, w["a"], w["b"], w["c"], w["inputs"], w["aux"], rb, sb), (hex(r_), hex(s_))
