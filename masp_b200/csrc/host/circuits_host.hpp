@@ -228,7 +228,7 @@ struct EdwardsPoint {
     static EdwardsPoint interpret(CS& cs, const AllocatedNum& u, const AllocatedNum& v) {
         AllocatedNum u2 = u.square(cs), v2 = v.square(cs);
         AllocatedNum u2v2 = u2.mul(cs, v2);
-        cs.enforce(LC(u2.var, K().minus_one).add(v2.var), LC(ONE, K().one), LC(ONE, K().one).add(u2v2.var, JJ().d));
+        MBH_ENFORCE(cs, LC(u2.var, K().minus_one).add(v2.var), LC(ONE, K().one), LC(ONE, K().one).add(u2v2.var, JJ().d));
         return {u, v};
     }
     static EdwardsPoint witness(CS& cs, const JPoint& p) {
@@ -251,10 +251,10 @@ struct EdwardsPoint {
         const Fr& d = JJ().d;
         Fr s = u.value + v.value;
         AllocatedNum t = AllocatedNum::alloc(cs, s.square());
-        cs.enforce(LC(u.var, K().one).add(v.var), LC(u.var, K().one).add(v.var), LC(t.var, K().one));
+        MBH_ENFORCE(cs, LC(u.var, K().one).add(v.var), LC(u.var, K().one).add(v.var), LC(t.var, K().one));
         AllocatedNum a = u.mul(cs, v);
         AllocatedNum c = AllocatedNum::alloc(cs, a.value.square() * d);
-        cs.enforce(LC(a.var, d), LC(a.var, K().one), LC(c.var, K().one));
+        MBH_ENFORCE(cs, LC(a.var, d), LC(a.var, K().one), LC(c.var, K().one));
         JPoint r;
         if (hint) {
             r = *hint;
@@ -267,19 +267,19 @@ struct EdwardsPoint {
             r = {a2 * (i * dm), (t.value - a2) * (i * dp)};
         }
         AllocatedNum u3 = AllocatedNum::alloc(cs, r.u);
-        cs.enforce(LC(ONE, K().one).add(c.var), LC(u3.var, K().one), LC(a.var, K().two));
+        MBH_ENFORCE(cs, LC(ONE, K().one).add(c.var), LC(u3.var, K().one), LC(a.var, K().two));
         AllocatedNum v3 = AllocatedNum::alloc(cs, r.v);
-        cs.enforce(LC(ONE, K().one).sub(c.var), LC(v3.var, K().one), LC(t.var, K().one).add(a.var, -K().two));
+        MBH_ENFORCE(cs, LC(ONE, K().one).sub(c.var), LC(v3.var, K().one), LC(t.var, K().one).add(a.var, -K().two));
         return {u3, v3};
     }
     EdwardsPoint add(CS& cs, const EdwardsPoint& o, const JPoint* hint = nullptr) const {
         const Fr& d = JJ().d;
         AllocatedNum big_u = AllocatedNum::alloc(cs, (u.value + v.value) * (o.u.value + o.v.value));
-        cs.enforce(LC(u.var, K().one).add(v.var), LC(o.u.var, K().one).add(o.v.var), LC(big_u.var, K().one));
+        MBH_ENFORCE(cs, LC(u.var, K().one).add(v.var), LC(o.u.var, K().one).add(o.v.var), LC(big_u.var, K().one));
         AllocatedNum a = o.v.mul(cs, u);
         AllocatedNum b = o.u.mul(cs, v);
         AllocatedNum c = AllocatedNum::alloc(cs, a.value * b.value * d);
-        cs.enforce(LC(a.var, d), LC(b.var, K().one), LC(c.var, K().one));
+        MBH_ENFORCE(cs, LC(a.var, d), LC(b.var, K().one), LC(c.var, K().one));
         JPoint r;
         if (hint) {
             r = *hint;
@@ -291,18 +291,18 @@ struct EdwardsPoint {
             r = {(a.value + b.value) * (i * dm), (big_u.value - a.value - b.value) * (i * dp)};
         }
         AllocatedNum u3 = AllocatedNum::alloc(cs, r.u);
-        cs.enforce(LC(ONE, K().one).add(c.var), LC(u3.var, K().one), LC(a.var, K().one).add(b.var));
+        MBH_ENFORCE(cs, LC(ONE, K().one).add(c.var), LC(u3.var, K().one), LC(a.var, K().one).add(b.var));
         AllocatedNum v3 = AllocatedNum::alloc(cs, r.v);
-        cs.enforce(LC(ONE, K().one).sub(c.var), LC(v3.var, K().one), LC(big_u.var, K().one).sub(a.var).sub(b.var));
+        MBH_ENFORCE(cs, LC(ONE, K().one).sub(c.var), LC(v3.var, K().one), LC(big_u.var, K().one).sub(a.var).sub(b.var));
         return {u3, v3};
     }
     EdwardsPoint conditionally_select(CS& cs, const Boolean& cond) const {
         AllocatedNum up = AllocatedNum::alloc(cs, cond.value() ? u.value : Fr::zero());
-        cs.enforce(LC(u.var, K().one), cond.lc(K().one), LC(up.var, K().one));
+        MBH_ENFORCE(cs, LC(u.var, K().one), cond.lc(K().one), LC(up.var, K().one));
         AllocatedNum vp = AllocatedNum::alloc(cs, cond.value() ? v.value : Fr::one());
         LC c(vp.var, K().one);
         c.sub(cond.not_().lc(K().one));
-        cs.enforce(LC(v.var, K().one), cond.lc(K().one), c);
+        MBH_ENFORCE(cs, LC(v.var, K().one), cond.lc(K().one), c);
         return {up, vp};
     }
     EdwardsPoint mul(CS& cs, const Bits& by) const {
@@ -361,12 +361,12 @@ struct MontgomeryPoint {
         Fr i = (y.value * xp).inverse();
         if (i.is_zero()) cs.failed = true;
         AllocatedNum u = AllocatedNum::alloc(cs, x.value * JJ().mont_scale * (i * xp));
-        cs.enforce(y.lc, LC(u.var, K().one), x.lc.scaled(JJ().mont_scale));
+        MBH_ENFORCE(cs, y.lc, LC(u.var, K().one), x.lc.scaled(JJ().mont_scale));
         AllocatedNum v = AllocatedNum::alloc(cs, (x.value - one) * (i * y.value));
         LC a = x.lc, c = x.lc;
         a.add(ONE, K().one);
         c.add(ONE, K().minus_one);
-        cs.enforce(a, LC(v.var, K().one), c);
+        MBH_ENFORCE(cs, a, LC(v.var, K().one), c);
         return {u, v};
     }
     MontgomeryPoint add(CS& cs, const MontgomeryPoint& o, const Fr* lam_hint = nullptr) const {
@@ -383,20 +383,20 @@ struct MontgomeryPoint {
             LC a = o.x.lc, c = o.y.lc;
             a.sub(x.lc);
             c.sub(y.lc);
-            cs.enforce(a, LC(lam.var, K().one), c);
+            MBH_ENFORCE(cs, a, LC(lam.var, K().one), c);
         }
         AllocatedNum xprime = AllocatedNum::alloc(cs, lam.value.square() - JJ().mont_a - x.value - o.x.value);
         {
             LC c(ONE, JJ().mont_a);
             c.add(x.lc).add(o.x.lc).add(xprime.var);
-            cs.enforce(LC(lam.var, K().one), LC(lam.var, K().one), c);
+            MBH_ENFORCE(cs, LC(lam.var, K().one), LC(lam.var, K().one), c);
         }
         AllocatedNum yprime = AllocatedNum::alloc(cs, -((xprime.value - x.value) * lam.value + y.value));
         {
             LC a = x.lc, c(yprime.var, K().one);
             a.sub(xprime.var);
             c.add(y.lc);
-            cs.enforce(a, LC(lam.var, K().one), c);
+            MBH_ENFORCE(cs, a, LC(lam.var, K().one), c);
         }
         return {Num::from_allocated(xprime), Num::from_allocated(yprime)};
     }
@@ -504,7 +504,7 @@ inline Bits merkle_and_anchor(CS& cs, AllocatedNum cur, const std::vector<AuthNo
     }
     cs.root = cur.value;
     AllocatedNum rt = AllocatedNum::alloc(cs, anchor);
-    cs.enforce(LC(cur.var, K().one).sub(rt.var), value_num.lc, LC());
+    MBH_ENFORCE(cs, LC(cur.var, K().one).sub(rt.var), value_num.lc, LC());
     rt.inputize(cs);
     return position_bits;
 }

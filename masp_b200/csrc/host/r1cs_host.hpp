@@ -129,6 +129,12 @@ struct CS {
         }
     }
 };
+// In a witness pass the three linear combinations are not even constructed.
+#define MBH_ENFORCE(cs, a, b, c)          \
+    do {                                  \
+        if (::mbh::recording()) (cs).enforce(a, b, c); \
+        else ++(cs).n_constraints;        \
+    } while (0)
 
 // ---------------------------------------------------------------------------
 // booleans
@@ -138,36 +144,36 @@ struct AllocatedBit {
     bool value;
     static AllocatedBit alloc(CS& cs, bool value) {
         Var v = cs.alloc(value ? K().one : Fr::zero());
-        cs.enforce(LC(ONE, K().one).sub(v), LC(v, K().one), LC());
+        MBH_ENFORCE(cs, LC(ONE, K().one).sub(v), LC(v, K().one), LC());
         return {v, value};
     }
     static AllocatedBit alloc_conditionally(CS& cs, bool value, const AllocatedBit& must_be_false) {
         Var v = cs.alloc(value ? K().one : Fr::zero());
-        cs.enforce(LC(ONE, K().one).sub(must_be_false.var).sub(v), LC(v, K().one), LC());
+        MBH_ENFORCE(cs, LC(ONE, K().one).sub(must_be_false.var).sub(v), LC(v, K().one), LC());
         return {v, value};
     }
     static AllocatedBit and_(CS& cs, const AllocatedBit& a, const AllocatedBit& b) {
         bool val = a.value && b.value;
         Var v = cs.alloc(val ? K().one : Fr::zero());
-        cs.enforce(LC(a.var, K().one), LC(b.var, K().one), LC(v, K().one));
+        MBH_ENFORCE(cs, LC(a.var, K().one), LC(b.var, K().one), LC(v, K().one));
         return {v, val};
     }
     static AllocatedBit and_not(CS& cs, const AllocatedBit& a, const AllocatedBit& b) {
         bool val = a.value && !b.value;
         Var v = cs.alloc(val ? K().one : Fr::zero());
-        cs.enforce(LC(a.var, K().one), LC(ONE, K().one).sub(b.var), LC(v, K().one));
+        MBH_ENFORCE(cs, LC(a.var, K().one), LC(ONE, K().one).sub(b.var), LC(v, K().one));
         return {v, val};
     }
     static AllocatedBit nor(CS& cs, const AllocatedBit& a, const AllocatedBit& b) {
         bool val = !a.value && !b.value;
         Var v = cs.alloc(val ? K().one : Fr::zero());
-        cs.enforce(LC(ONE, K().one).sub(a.var), LC(ONE, K().one).sub(b.var), LC(v, K().one));
+        MBH_ENFORCE(cs, LC(ONE, K().one).sub(a.var), LC(ONE, K().one).sub(b.var), LC(v, K().one));
         return {v, val};
     }
     static AllocatedBit xor_(CS& cs, const AllocatedBit& a, const AllocatedBit& b) {
         bool val = a.value != b.value;
         Var v = cs.alloc(val ? K().one : Fr::zero());
-        cs.enforce(LC(a.var, K().two), LC(b.var, K().one), LC(a.var, K().one).add(b.var).sub(v));
+        MBH_ENFORCE(cs, LC(a.var, K().two), LC(b.var, K().one), LC(a.var, K().one).add(b.var).sub(v));
         return {v, val};
     }
 };
@@ -223,7 +229,7 @@ struct Boolean {
         }
         LC c = a.lc(K().one);
         c.sub(b.lc(K().one));
-        cs.enforce(LC(), LC(), c);
+        MBH_ENFORCE(cs, LC(), LC(), c);
     }
 };
 typedef std::vector<Boolean> Bits;
@@ -251,29 +257,29 @@ struct AllocatedNum {
     static AllocatedNum alloc(CS& cs, const Fr& v) { return {cs.alloc(v), v}; }
     AllocatedNum mul(CS& cs, const AllocatedNum& o) const {
         AllocatedNum out = alloc(cs, value * o.value);
-        cs.enforce(LC(var, K().one), LC(o.var, K().one), LC(out.var, K().one));
+        MBH_ENFORCE(cs, LC(var, K().one), LC(o.var, K().one), LC(out.var, K().one));
         return out;
     }
     AllocatedNum square(CS& cs) const {
         AllocatedNum out = alloc(cs, value.square());
-        cs.enforce(LC(var, K().one), LC(var, K().one), LC(out.var, K().one));
+        MBH_ENFORCE(cs, LC(var, K().one), LC(var, K().one), LC(out.var, K().one));
         return out;
     }
     void assert_nonzero(CS& cs) const {
         if (value.is_zero()) cs.failed = true;
         Var inv = cs.alloc(value.inverse());
-        cs.enforce(LC(var, K().one), LC(inv, K().one), LC(ONE, K().one));
+        MBH_ENFORCE(cs, LC(var, K().one), LC(inv, K().one), LC(ONE, K().one));
     }
     void inputize(CS& cs) const {
         Var inp = cs.alloc_input(value);
-        cs.enforce(LC(inp, K().one), LC(ONE, K().one), LC(var, K().one));
+        MBH_ENFORCE(cs, LC(inp, K().one), LC(ONE, K().one), LC(var, K().one));
     }
     static void conditionally_reverse(CS& cs, const AllocatedNum& a, const AllocatedNum& b, const Boolean& cond,
                                       AllocatedNum& c, AllocatedNum& d) {
         c = alloc(cs, cond.value() ? b.value : a.value);
-        cs.enforce(LC(a.var, K().one).sub(b.var), cond.lc(K().one), LC(a.var, K().one).sub(c.var));
+        MBH_ENFORCE(cs, LC(a.var, K().one).sub(b.var), cond.lc(K().one), LC(a.var, K().one).sub(c.var));
         d = alloc(cs, cond.value() ? a.value : b.value);
-        cs.enforce(LC(b.var, K().one).sub(a.var), cond.lc(K().one), LC(b.var, K().one).sub(d.var));
+        MBH_ENFORCE(cs, LC(b.var, K().one).sub(a.var), cond.lc(K().one), LC(b.var, K().one).sub(d.var));
     }
     Bits to_bits_le(CS& cs) const {
         uint64_t w[4];
@@ -286,7 +292,7 @@ struct AllocatedNum {
             bits.push_back(Boolean::from_bit(b));
         }
         lc.sub(var);
-        cs.enforce(LC(), LC(), lc);
+        MBH_ENFORCE(cs, LC(), LC(), lc);
         return bits;
     }
     // bits of the value with the proof that they encode an integer <= r - 1
@@ -323,7 +329,7 @@ struct AllocatedNum {
             out[i] = Boolean::from_bit(b);
         }
         lc.sub(var);
-        cs.enforce(LC(), LC(), lc);
+        MBH_ENFORCE(cs, LC(), LC(), lc);
         return out;
     }
 };
@@ -385,7 +391,7 @@ inline void lookup3_xy(CS& cs, const Boolean bits[3], const Window8& w, Allocate
             bits[2].add_to(c, -co[4]);
             precomp.add_to(c, -co[6]);
         }
-        cs.enforce(a, bits[0].lc(K().one), c);
+        MBH_ENFORCE(cs, a, bits[0].lc(K().one), c);
     }
 }
 
@@ -411,7 +417,7 @@ inline void lookup3_xy_with_conditional_negation(CS& cs, const Boolean bits[3], 
     a.add(y_lc);
     LC c = y_lc;
     c.sub(ya.var);
-    cs.enforce(a, bits[2].lc(K().one), c);
+    MBH_ENFORCE(cs, a, bits[2].lc(K().one), c);
     y = Num::from_allocated(ya);
 }
 
@@ -421,7 +427,7 @@ inline void pack_into_inputs(CS& cs, const Bits& bits) {
         Num num;
         for (size_t j = k; j < bits.size() && j < k + 254; ++j) num.add_bool_with_coeff(bits[j], K().pow2[j - k]);
         Var inp = cs.alloc_input(num.value);
-        cs.enforce(num.lc, LC(ONE, K().one), LC(inp, K().one));
+        MBH_ENFORCE(cs, num.lc, LC(ONE, K().one), LC(inp, K().one));
     }
 }
 
@@ -434,7 +440,7 @@ struct MultiEq {
     LC lhs, rhs;
     explicit MultiEq(CS& c) : cs(c) {}
     void accumulate() {
-        cs.enforce(lhs, LC(ONE, K().one), rhs);
+        MBH_ENFORCE(cs, lhs, LC(ONE, K().one), rhs);
         lhs = LC();
         rhs = LC();
         bits_used = 0;
