@@ -293,10 +293,30 @@ def _verify_file_size(path, expected, name):
         raise ParameterError("%s parameter file size is not correct: %d, expected %d" % (name, size, expected))
 
 
+def masp_circuits():
+    """The three recorded circuits (masp_b200.circuits.Circuit), built once per process."""
+    global _circuits
+    if _circuits is None:
+        from . import circuits as C
+        _circuits = {"spend": C.Circuit(C.SPEND), "output": C.Circuit(C.OUTPUT), "convert": C.Circuit(C.CONVERT)}
+    return _circuits
+
+
+_circuits = None
+
+
 def parse_parameters(spend_bytes, output_bytes, convert_bytes, densities=None, verify_hashes=True):
     """parse_parameters (masp_proofs/src/lib.rs:330-403): Parameters::read on each
     stream, then the whole stream -- including the MPC transcript after the
-    key -- is BLAKE2b-512 hashed and compared with the pinned constants."""
+    key -- is BLAKE2b-512 hashed and compared with the pinned constants.
+
+    densities=None (the reference's signature has no such argument): the
+    bitmaps come from the library's own recorded circuits, which are then bound
+    to the keys so that the *_proof methods accept circuit instances."""
+    bind = densities is None
+    if bind:
+        circs = masp_circuits()
+        densities = {k: c.densities() for k, c in circs.items()}
     dens = densities or {}
     out = {}
     for name, buf, want in (("spend", spend_bytes, MASP_SPEND_HASH), ("output", output_bytes, MASP_OUTPUT_HASH),
@@ -306,6 +326,8 @@ def parse_parameters(spend_bytes, output_bytes, convert_bytes, densities=None, v
             if got != want:
                 raise ParameterError("MASP %s parameter file is not correct (BLAKE2b %s...)" % (name, got[:16]))
         out[name] = Parameters.read(buf, dens.get(name))
+        if bind:
+            out[name].bind_circuit(circs[name])
     return out
 
 
@@ -351,15 +373,34 @@ class LocalTxProver:
             return None  # the reference returns None (prover.rs:120-136)
         return cls.new(*paths, densities=densities)
 
-    # Each returns the [u8; 192] zkproof of the description.
-    def spend_proof(self, assignment, rng=_os_rng_scalar):
-        return create_random_proof(assignment, self.spend_params, rng)
+    # Each returns the [u8; 192] zkproof of the description.  `instance` is either the
+    # ProvingAssignment a caller synthesised itself, or the circuit instance the reference hands
+    # to create_random_proof (masp_b200.circuits.Spend / Output / Convert) when the keys were
+    # loaded with the library's own circuits bound (densities=None).
+    @staticmethod
+    def _prove(instance, params, rng, check):
+        if isinstance(instance, ProvingAssignment):
+            return create_random_proof(instance, params, rng)
+        circ = getattr(params, "circuit", None)
+        if circ is None:
+            raise ValueError("these parameters have no circuit bound; pass a ProvingAssignment")
+        inputs, aux = circ.synthesize([instance])
+        if check:  # verify_proof right after proving, as sapling/prover.rs:148 and :266 do
+            set_option("verify", 1)
+        try:
+            return create_proof_batch_from_witness(params, inputs, aux, [rng()], [rng()])[0]
+        finally:
+            if check:
+                set_option("verify", 0)
 
-    def output_proof(self, assignment, rng=_os_rng_scalar):
-        return create_random_proof(assignment, self.output_params, rng)
+    def spend_proof(self, instance, rng=_os_rng_scalar):
+        return self._prove(instance, self.spend_params, rng, True)
 
-    def convert_proof(self, assignment, rng=_os_rng_scalar):
-        return create_random_proof(assignment, self.convert_params, rng)
+    def output_proof(self, instance, rng=_os_rng_scalar):
+        return self._prove(instance, self.output_params, rng, False)   # the reference does not self-check outputs
+
+    def convert_proof(self, instance, rng=_os_rng_scalar):
+        return self._prove(instance, self.convert_params, rng, True)
 
     def prove_bundle(self, spends=(), converts=(), outputs=(), rng=_os_rng_scalar):
         """All descriptions of a transaction in one launch per circuit (the
@@ -369,7 +410,13 @@ class LocalTxProver:
                               (self.output_params, outputs)):
             group = list(group)
             pairs = [(rng(), rng()) for _ in group]  # r then s for each description, in order
-            res.append(create_proof_batch(group, params, [p[0] for p in pairs], [p[1] for p in pairs]))
+            if group and not isinstance(group[0], ProvingAssignment):
+                # circuit instances: one witness pass on the host cores, rows on the device
+                inputs, aux = params.circuit.synthesize(group)
+                res.append(create_proof_batch_from_witness(params, inputs, aux, [p[0] for p in pairs],
+                                                           [p[1] for p in pairs]))
+            else:
+                res.append(create_proof_batch(group, params, [p[0] for p in pairs], [p[1] for p in pairs]))
         return tuple(res)
 
 

@@ -197,3 +197,34 @@ def test_witness_only_proofs_gpu(gpu, oracle, name, kind):
     wrong = list(cs.inputs[1:])
     wrong[0] = (wrong[0] + 1) % R
     assert not verify_with_pairing(key, proofs[0], wrong)
+
+
+@pytest.mark.gpu
+def test_local_tx_prover_with_circuit_instances_gpu(gpu, oracle):
+    """LocalTxProver::from_bytes(spend, output, convert) with the reference's signature (no density
+    argument: the library's recorded circuits supply them) and *_proof called with circuit
+    instances, Output and Convert under keys with a known trapdoor so that the proofs verify."""
+    from test_circuits import real_instance, verify_with_pairing, VALUE, RCV, RCM, ESK, PATH
+    from test_circuits import G_D as GD
+    cs_o, key_o, _, _ = real_instance("output")
+    cs_c, key_c, _, _ = real_instance("convert")
+    spend_key = gpu.params_synthesize(syn.SPEND)  # a key of the right shape; Spend is not proved here
+    prover = gpu.LocalTxProver.from_bytes(spend_key, key_o, key_c, verify_hashes=False)
+    assert prover.output_params.circuit.hash() == C.PINS[C.OUTPUT][2]
+    ident, ag = mc.find_asset()
+    vc = C.ValueCommitmentOpening(ag, VALUE, RCV)
+    out_inst = C.Output(vc, ident, GD, mc.jj_mul(GD, 999), RCM, ESK)
+    conv_inst = C.Convert(vc, PATH, mc.convert_native_anchor(ag, PATH))
+    p_out = prover.output_proof(out_inst)
+    p_conv = prover.convert_proof(conv_inst)       # runs verify_proof on the device, like the reference
+    assert verify_with_pairing(key_o, p_out, cs_o.inputs[1:])
+    assert verify_with_pairing(key_c, p_conv, cs_c.inputs[1:])
+    assert gpu.verify_proofs(prover.convert_params, [p_conv, p_out], [cs_c.inputs[1:]] * 2) == [True, False]
+    # a convert instance whose anchor is not the path's root cannot be proved: Err(()) in the reference
+    bad = C.Convert(vc, PATH, (conv_inst.anchor + 1) % R)
+    with pytest.raises(gpu.Mb200Error) as e:
+        prover.convert_proof(bad)
+    assert e.value.code == -8
+    _, conv, outs = prover.prove_bundle(converts=[conv_inst, conv_inst], outputs=[out_inst])
+    assert all(verify_with_pairing(key_c, p, cs_c.inputs[1:]) for p in conv) and len(set(conv)) == 2
+    assert verify_with_pairing(key_o, outs[0], cs_o.inputs[1:])
