@@ -53,6 +53,14 @@ def _check(pv):
         assert e.value.code == -8
     finally:
         pv.set_option("verify", 0)
+    # bilinearity, as a property of the device pairing: (k A, k^-1 B, C) satisfies the same equation
+    a_pt, b_pt, c_pt = g.proof_read(proof)
+    k = 0x1D2C3B4A5968778695A4B3C2D1E0F
+    ka = G1.to_affine(G1.mul(G1.from_affine(a_pt), k))
+    kb = G2.to_affine(G2.mul(G2.from_affine(b_pt), pow(k, R - 2, R)))
+    kb_bad = G2.to_affine(G2.mul(G2.from_affine(b_pt), pow(k + 1, R - 2, R)))
+    enc = lambda A, B, Cc: G1.encode_uncompressed(A) + G2.encode_uncompressed(B) + G1.encode_uncompressed(Cc)
+    assert pv.verify_batch(P, [enc(ka, kb, c_pt), enc(ka, kb_bad, c_pt)], [inputs[1:]] * 2) == [True, False]
     # proofs in wire form: Proof::read (decompression, subgroup checks) happens on the device
     flipped = bytearray(proof)
     flipped[0] ^= 0x20                          # the other square root for A: a valid point, wrong proof
