@@ -199,10 +199,11 @@ def circuit_path(pv, key, shape, n, rounds, seed=20261017, torch=None):
     th.join()
     t_pipe = time.perf_counter() - t0
 
-    def pipelined():
-        """One more pipelined pass (used for the variant with the self-check on)."""
+    def pipelined(in_flight=4):
+        """One more pipelined pass (used for the variant with the self-check on: a batch is only
+        complete after its check, so two more batches are kept in flight to cover that latency)."""
         qq, fr = queue.Queue(maxsize=1), queue.Queue()
-        for b in ring:
+        for b in ring + [(pinned(n * circ.n_inputs * 32), pinned(n * circ.n_aux * 32)) for _ in range(in_flight - 2)]:
             fr.put(b)
 
         def prod():
@@ -216,7 +217,7 @@ def circuit_path(pv, key, shape, n, rounds, seed=20261017, torch=None):
             i_k, a_k = qq.get()
             kp.append((i_k, a_k))
             tk.append(pv.prove_submit_witness(params, n, i_k, a_k, r_b, s_b, outs[k]))
-            if len(tk) > 2:
+            if len(tk) > in_flight:
                 pv.prove_wait(tk.pop(0))
                 fr.put(kp.pop(0))
         while tk:

@@ -14,9 +14,13 @@ for name in sys.argv[1:] or ["output", "convert", "spend"]:
     P = pv.Parameters.read(pv.params_synthesize(sh), sh.densities())
     w = syn.witness(sh, 0, pv.fr_mul)
     a = pv.ProvingAssignment(w["a"], w["b"], w["c"], w["inputs"], w["aux"])
-    for i in range(3):
+    wall, dev = [], []
+    for i in range(12):  # the first calls pay buffer growth and clock ramp-up; report the settled figures
         t0 = time.perf_counter()
         pv.create_proof(a, P, w["r"], w["s"])
-        print(name, "wall %.1f ms" % ((time.perf_counter() - t0) * 1e3),
-              "device %.1f ms" % (pv.get_counter("last_batch_us") / 1e3), flush=True)
+        wall.append((time.perf_counter() - t0) * 1e3)
+        dev.append(pv.get_counter("last_batch_us") / 1e3)
+    wall, dev = sorted(wall[2:]), sorted(dev[2:])
+    print(name, "wall min %.1f median %.1f ms" % (wall[0], wall[len(wall) // 2]),
+          "device min %.1f median %.1f ms" % (dev[0], dev[len(dev) // 2]), flush=True)
     del P
