@@ -142,6 +142,11 @@ struct Reader {
         memcpy(w, p, 32);
         p += 32;
     }
+    // a Jubjub scalar: the circuits allocate 252 bits for it (JUBJUB_FR_BITS), anything above is an error
+    void jscalar(uint64_t w[4]) {
+        words(w);
+        if (w[3] >> 60) ok = false;
+    }
     uint64_t u64() {
         uint64_t w[4];
         words(w);
@@ -174,13 +179,13 @@ bool run_circuit(CS& cs, int kind, uint32_t depth, const uint8_t* w) {
     if (kind == MB200_CIRCUIT_SPEND) {
         SpendWitness s;
         s.ak = r.point();
-        r.words(s.nsk);
+        r.jscalar(s.nsk);
         s.g_d = r.point();
         s.asset_generator = r.point();
         s.value = r.u64();
-        r.words(s.rcv);
-        r.words(s.rcm);
-        r.words(s.ar);
+        r.jscalar(s.rcv);
+        r.jscalar(s.rcm);
+        r.jscalar(s.ar);
         s.anchor = r.fr();
         r.path(depth, s.path);
         if (!r.ok) return false;
@@ -191,18 +196,18 @@ bool run_circuit(CS& cs, int kind, uint32_t depth, const uint8_t* w) {
         r.p += 32;
         o.asset_generator = r.point();
         o.value = r.u64();
-        r.words(o.rcv);
+        r.jscalar(o.rcv);
         o.g_d = r.point();
         o.pk_d = r.point();
-        r.words(o.rcm);
-        r.words(o.esk);
+        r.jscalar(o.rcm);
+        r.jscalar(o.esk);
         if (!r.ok) return false;
         output_circuit(cs, o);
     } else {
         ConvertWitness c;
         c.asset_generator = r.point();
         c.value = r.u64();
-        r.words(c.rcv);
+        r.jscalar(c.rcv);
         c.anchor = r.fr();
         r.path(depth, c.path);
         if (!r.ok) return false;
