@@ -277,6 +277,10 @@ struct Mont {
         for (int i = 0; i < N; ++i) s.v[i] = borrow ? s.v[i] : t.v[i];
         return s;
     }
+    // (A dedicated squaring -- cross products once, product-scanning reduction, 222 instead of 288
+    // wide multiplies -- is exact but measured 2 % SLOWER inside the accumulation kernel: its
+    // three-word column accumulator serialises what the row-wise form leaves independent.
+    // Kept with its test under scripts/microbench/sqr_ps.cuh.)
     MB_HD static Mont sqr(const Mont& a) { return mul(a, a); }
 
     // reference multiplication with 64-bit temporaries (self-test only)
