@@ -137,6 +137,70 @@ struct Jubjub {
         return !bad;
     }
 
+    // Everything a Pedersen hash needs from the field's division, for all of its segments at once:
+    // per window the slope of its chain step, per segment the Edwards image of the segment sum and
+    // the running Edwards sum.  Three inversions per hash (all slope denominators and segment Z's;
+    // the Montgomery -> Edwards denominators; the running sums), however many segments it has.
+    struct PedersenPlan {
+        std::vector<Fr> lam;         // per window (first window of a segment: unused)
+        std::vector<JPoint> seg_ed;  // per segment: into_edwards of the segment's sum
+        std::vector<JPoint> run_ed;  // per segment: seg_ed[0] + ... + seg_ed[s]
+        bool ok = true;
+    };
+    // tx, ty: the window points of the whole hash; seg_len[s] windows belong to segment s
+    void pedersen_plan(const std::vector<Fr>& tx, const std::vector<Fr>& ty, const std::vector<size_t>& seg_len,
+                       PedersenPlan& plan) const {
+        const size_t nw = tx.size(), ns = seg_len.size();
+        std::vector<Fr> u(nw), den(nw + ns), scratch;  // den: v per window, then Z per segment
+        std::vector<Fr> fx(ns), fy(ns);                // projective numerators of the segment sums
+        size_t base = 0;
+        for (size_t sgm = 0; sgm < ns; ++sgm) {
+            size_t n = seg_len[sgm];
+            Fr X = tx[base], Y = ty[base], Z = Fr::one();
+            den[base] = Fr::one();
+            for (size_t k = 1; k < n; ++k) {
+                const Fr &x2 = tx[base + k], &y2 = ty[base + k];
+                Fr x2z = x2 * Z;
+                Fr uu = y2 * Z - Y, v1 = x2z - X;
+                u[base + k] = uu;
+                den[base + k] = v1;
+                Fr vv = v1.square(), vvv = vv * v1;
+                Fr W = uu.square() * Z - vv * (mont_a * Z + x2z + X);
+                Fr Xn = W * v1;
+                Y = uu * (X * vv - W) - Y * vvv;
+                X = Xn;
+                Z = vvv * Z;
+            }
+            fx[sgm] = X;
+            fy[sgm] = Y;
+            den[nw + sgm] = Z;
+            base += n;
+        }
+        if (batch_inverse(den.data(), nw + ns, scratch)) plan.ok = false;
+        plan.lam.assign(nw, Fr::zero());
+        base = 0;
+        for (size_t sgm = 0; sgm < ns; ++sgm) {
+            for (size_t k = 1; k < seg_len[sgm]; ++k) plan.lam[base + k] = u[base + k] * den[base + k];
+            base += seg_len[sgm];
+        }
+        // Montgomery -> Edwards for every segment sum: u = scale x / y, v = (x - 1) / (x + 1)
+        std::vector<Fr> sx(ns), sy(ns), d2(ns);
+        Fr one = Fr::one();
+        for (size_t sgm = 0; sgm < ns; ++sgm) {
+            sx[sgm] = fx[sgm] * den[nw + sgm];
+            sy[sgm] = fy[sgm] * den[nw + sgm];
+            d2[sgm] = sy[sgm] * (sx[sgm] + one);
+        }
+        if (batch_inverse(d2.data(), ns, scratch)) plan.ok = false;
+        plan.seg_ed.resize(ns);
+        for (size_t sgm = 0; sgm < ns; ++sgm) {
+            Fr xp = sx[sgm] + one;
+            plan.seg_ed[sgm] = {sx[sgm] * mont_scale * (d2[sgm] * xp), (sx[sgm] - one) * (d2[sgm] * sy[sgm])};
+        }
+        plan.run_ed.resize(ns);
+        chain_sums(plan.seg_ed.data(), ns, plan.run_ed.data());
+    }
+
     bool to_montgomery(const JPoint& p, Fr& x, Fr& y) const {  // constants.rs:100-141
         Fr one = Fr::one();
         if (p.v == one) return false;
@@ -354,15 +418,21 @@ inline EdwardsPoint fixed_base_multiplication(CS& cs, Jubjub::Fixed gen, const B
 
 struct MontgomeryPoint {
     Num x, y;
-    EdwardsPoint into_edwards(CS& cs) const {
-        Fr one = Fr::one();
-        // one inversion for 1 / y and 1 / (x + 1)
-        Fr xp = x.value + one;
-        Fr i = (y.value * xp).inverse();
-        if (i.is_zero()) cs.failed = true;
-        AllocatedNum u = AllocatedNum::alloc(cs, x.value * JJ().mont_scale * (i * xp));
+    EdwardsPoint into_edwards(CS& cs, const JPoint* hint = nullptr) const {
+        JPoint r;
+        if (hint) {
+            r = *hint;
+        } else {
+            Fr one = Fr::one();
+            // one inversion for 1 / y and 1 / (x + 1)
+            Fr xp = x.value + one;
+            Fr i = (y.value * xp).inverse();
+            if (i.is_zero()) cs.failed = true;
+            r = {x.value * JJ().mont_scale * (i * xp), (x.value - one) * (i * y.value)};
+        }
+        AllocatedNum u = AllocatedNum::alloc(cs, r.u);
         MBH_ENFORCE(cs, y.lc, LC(u.var, K().one), x.lc.scaled(JJ().mont_scale));
-        AllocatedNum v = AllocatedNum::alloc(cs, (x.value - one) * (i * y.value));
+        AllocatedNum v = AllocatedNum::alloc(cs, r.v);
         LC a = x.lc, c = x.lc;
         a.add(ONE, K().one);
         c.add(ONE, K().minus_one);
@@ -407,38 +477,37 @@ inline EdwardsPoint pedersen_hash(CS& cs, const bool personalization[6], const B
     for (int i = 0; i < 6; ++i) all.push_back(Boolean::constant(personalization[i]));
     all.insert(all.end(), bits.begin(), bits.end());
     Boolean f = Boolean::constant(false);
+    // pre-pass over the whole hash: window points from the tables, then every division it needs
+    const size_t nw = (all.size() + 2) / 3;
+    std::vector<Fr> tx(nw), ty(nw);
+    std::vector<size_t> seg_len;
+    for (size_t k = 0; k < nw; ++k) {
+        size_t seg = k / 63, w = k % 63, q = 3 * k;
+        if (w == 0) seg_len.push_back(0);
+        ++seg_len.back();
+        const Window4& win = JJ().pedersen[seg][w];
+        int idx = (all[q].value() ? 1 : 0) | (q + 1 < all.size() && all[q + 1].value() ? 2 : 0);
+        tx[k] = win.x[idx];
+        ty[k] = (q + 2 < all.size() && all[q + 2].value()) ? -win.y[idx] : win.y[idx];
+    }
+    Jubjub::PedersenPlan plan;
+    JJ().pedersen_plan(tx, ty, seg_len, plan);
+    if (!plan.ok) cs.failed = true;
+
     EdwardsPoint edwards_result;
-    bool have_result = false;
-    size_t pos = 0;
-    int seg = 0;
-    while (pos < all.size()) {
+    size_t pos = 0, k = 0;
+    for (size_t seg = 0; seg < seg_len.size(); ++seg) {
         MontgomeryPoint segment_result;
-        bool have_seg = false;
         const std::vector<Window4>& windows = JJ().pedersen[seg];
-        // pre-pass: this segment's window points and the slope of every chain step
-        size_t nwin = std::min(windows.size(), (all.size() - pos + 2) / 3);
-        std::vector<Fr> tx(nwin), ty(nwin), lam(nwin);
-        for (size_t k = 0; k < nwin; ++k) {
-            size_t q = pos + 3 * k;
-            int idx = (all[q].value() ? 1 : 0) | (q + 1 < all.size() && all[q + 1].value() ? 2 : 0);
-            tx[k] = windows[k].x[idx];
-            ty[k] = (q + 2 < all.size() && all[q + 2].value()) ? -windows[k].y[idx] : windows[k].y[idx];
-        }
-        if (!JJ().montgomery_chain_slopes(tx.data(), ty.data(), nwin, lam.data())) cs.failed = true;
-        size_t w = 0;
-        while (pos < all.size()) {
+        for (size_t w = 0; w < seg_len[seg]; ++w, ++k) {
             Boolean chunk[3] = {all[pos], pos + 1 < all.size() ? all[pos + 1] : f, pos + 2 < all.size() ? all[pos + 2] : f};
             pos += 3;
             MontgomeryPoint tmp;
             lookup3_xy_with_conditional_negation(cs, chunk, windows[w], tmp.x, tmp.y);
-            segment_result = have_seg ? tmp.add(cs, segment_result, &lam[w]) : tmp;
-            have_seg = true;
-            if (++w == windows.size()) break;
+            segment_result = w ? tmp.add(cs, segment_result, &plan.lam[k]) : tmp;
         }
-        EdwardsPoint se = segment_result.into_edwards(cs);
-        edwards_result = have_result ? se.add(cs, edwards_result) : se;
-        have_result = true;
-        ++seg;
+        EdwardsPoint se = segment_result.into_edwards(cs, &plan.seg_ed[seg]);
+        edwards_result = seg ? se.add(cs, edwards_result, &plan.run_ed[seg]) : se;
     }
     return edwards_result;
 }
