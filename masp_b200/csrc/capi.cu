@@ -289,7 +289,9 @@ static uint64_t prove_submit(const Params& P, size_t n_proofs, size_t rows, cons
 #endif
     } catch (...) {
 #ifndef MB200_EMU
+        // nothing of this batch may still be running when its buffers go back to the pool
         for (auto& x : g.ctxs) cudaStreamSynchronize(x.stream);
+        for (auto& v : g.vstream) cudaStreamSynchronize(v);
 #endif
         ticket_destroy(t);
         throw;

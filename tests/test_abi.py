@@ -66,3 +66,20 @@ def test_product_package_never_imports_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text and "oracle/c" not in text, f
                 assert "libmasp_b200_emu" not in text or f == "build.py", f
+
+
+def test_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line
+    with the contract's keys; one bounded step of one Spend-shaped proof on this box's cores."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--ref-sample", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-1000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "spend_proofs_per_sec" and line["unit"] == "proofs/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
