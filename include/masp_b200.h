@@ -181,6 +181,14 @@ int mb200_verify_batch(const mb200_params* p, size_t n, const uint8_t* proofs_un
  * subgroup -- and a proof that does not read is simply not accepted (ok_out[i] = 0), as at the
  * verifier's call sites masp_proofs/src/sapling/verifier/single.rs:60, 77, 93. */
 int mb200_verify_proofs(const mb200_params* p, size_t n, const uint8_t* proofs, const uint8_t* inputs, uint8_t* ok_out);
+/* The randomised batch check of bellman's groth16::batch::Verifier (the reference's BatchValidator,
+ * masp_proofs/src/sapling/verifier/batch.rs:24-31, 85-160): one verdict for the whole batch, n + 3
+ * Miller loops and a single final exponentiation.  z: n x 16 bytes of caller-drawn randomness (the
+ * 128-bit coefficients; drawn by the caller like r and s, so a run is reproducible).  *all_ok = 1
+ * iff every proof reads and the combined equation holds; an invalid proof passes only with
+ * probability about 2^-128 over z. */
+int mb200_verify_proofs_batch(const mb200_params* p, size_t n, const uint8_t* proofs, const uint8_t* inputs,
+                              const uint8_t* z, int* all_ok);
 
 /* multiexp over arbitrary bases (ec-gpu-gen `multiexp`, full density);
  * result uncompressed.  No table is precomputed on this path. */

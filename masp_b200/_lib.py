@@ -18,7 +18,7 @@ SYMBOLS = [
     "mb200_fr_mul_device", "mb200_set_option", "mb200_get_counter", "mb200_selftest", "mb200_bench_fpmul", "mb200_bench_latency",
     "mb200_strerror", "mb200_last_error",
     "mb200_circuit_new", "mb200_circuit_free", "mb200_circuit_info", "mb200_circuit_hash", "mb200_circuit_densities",
-    "mb200_circuit_matrix", "mb200_circuit_synthesize", "mb200_circuit_rows", "mb200_circuit_root", "mb200_params_bind_circuit", "mb200_prove_batch_witness", "mb200_verify_batch", "mb200_verify_proofs",
+    "mb200_circuit_matrix", "mb200_circuit_synthesize", "mb200_circuit_rows", "mb200_circuit_root", "mb200_params_bind_circuit", "mb200_prove_batch_witness", "mb200_verify_batch", "mb200_verify_proofs", "mb200_verify_proofs_batch",
 ]
 
 
@@ -79,6 +79,7 @@ def bind(path):
     L.mb200_params_bind_circuit.argtypes = [vp, vp]
     L.mb200_verify_batch.argtypes = [vp, sz, vp, vp, vp]
     L.mb200_verify_proofs.argtypes = [vp, sz, vp, vp, vp]
+    L.mb200_verify_proofs_batch.argtypes = [vp, sz, vp, vp, vp, c.POINTER(c.c_int)]
     L.mb200_prove_batch_witness.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.mb200_strerror.argtypes = [c.c_int]
     L.mb200_strerror.restype = u8p

@@ -719,6 +719,54 @@ int mb200_verify_proofs(const mb200_params* p, size_t n, const uint8_t* proofs, 
     MB_API_END
 }
 
+int mb200_verify_proofs_batch(const mb200_params* p, size_t n, const uint8_t* proofs, const uint8_t* inputs,
+                              const uint8_t* z, int* all_ok) {
+    MB_API_BEGIN
+    require_init();
+    if (!p || !p->p || !all_ok || (n && (!proofs || !inputs || !z))) fail(MB200_EINVAL, "null argument%s", "");
+    *all_ok = 1;
+    if (n == 0) return MB200_OK;
+    const Params& P = *p->p;
+    DevBuf raw(n * 192), pa(n * sizeof(G1Affine)), pb(n * sizeof(G2Affine)), pc(n * sizeof(G1Affine)), bad(n * 4),
+        flag(4), din(n * P.n_inputs * 32), dz(n * 16), f(n * sizeof(Fp12)), zc(n * sizeof(G1XYZZ)),
+        zx(n * P.n_inputs * sizeof(Fr)), ok(4);
+    copy_h2d(raw.p, proofs, n * 192, g.main);
+    copy_h2d(din.p, inputs, n * P.n_inputs * 32, g.main);
+    copy_h2d(dz.p, z, n * 16, g.main);
+    dev_memset(bad.p, 0, n * 4, g.main);
+    dev_memset(flag.p, 0, 4, g.main);
+    ProofReadArgs ra{n * 3, raw.as<uint8_t>(), pa.as<G1Affine>(), pb.as<G2Affine>(), pc.as<G1Affine>(), bad.as<uint32_t>()};
+    launch_proof_read(ra, g.main);
+    check_scalars_dev(din.as<Fr>(), n * P.n_inputs, 0, 1, flag.as<uint32_t>(), g.main);
+    BatchMillerArgs ma{n, pa.as<G1Affine>(), pb.as<G2Affine>(), pc.as<G1Affine>(), din.as<uint32_t>(), P.n_inputs,
+                       dz.as<uint32_t>(), f.as<Fp12>(), zc.as<G1XYZZ>(), zx.as<Fr>()};
+    launch_batch_miller(ma, g.main);
+    BatchFinalArgs fa;
+    fa.nthreads = 1;
+    fa.n = n;
+    fa.f = f.as<Fp12>();
+    fa.zc = zc.as<G1XYZZ>();
+    fa.zx = zx.as<Fr>();
+    fa.n_inputs = P.n_inputs;
+    fa.alpha = P.vk_g1.as<G1Affine>();
+    fa.beta = P.vk_g2.as<G2Affine>();
+    fa.vk = {P.vk_ic.as<G1Affine>(), P.vk_g2.as<G2Affine>() + 1, P.vk_g2.as<G2Affine>() + 2, P.vk_ab.as<Fp12>()};
+    fa.ok = ok.as<uint32_t>();
+    launch_batch_final(fa, g.main);
+    std::vector<uint32_t> hbad(n);
+    uint32_t hok = 0, hflag = 0;
+    copy_d2h(&hok, ok.p, 4, g.main);
+    copy_d2h(hbad.data(), bad.p, n * 4, g.main);
+    copy_d2h(&hflag, flag.p, 4, g.main);
+    stream_sync(g.main);
+    if (hflag) fail(MB200_ESCALAR, "a public input is not canonical (>= r)%s", "");
+    int good = hok ? 1 : 0;
+    for (size_t i = 0; i < n; ++i)
+        if (hbad[i]) good = 0;
+    *all_ok = good;
+    MB_API_END
+}
+
 int mb200_prove_batch_witness(const mb200_params* p, size_t n_proofs, const uint8_t* inputs, const uint8_t* aux,
                               const uint8_t* r, const uint8_t* s, uint8_t* proofs_out) {
     MB_API_BEGIN

@@ -463,6 +463,84 @@ MB_HD void proof_read_body(const ProofReadArgs& a, size_t tid) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// randomised batch check (bellman groth16::batch::Verifier as used by
+// masp_proofs/src/sapling/verifier/batch.rs:24-31, 85-160): with random 128-bit z_i,
+//   prod_i e(z_i A_i, B_i) * e(-(sum_i z_i) alpha, beta) * e(-sum_j (sum_i z_i x_ij) IC_j, gamma)
+//                          * e(-sum_i z_i C_i, delta) = 1
+// holds for a batch of valid proofs and fails for any invalid one except with probability
+// ~2^-128: n + 3 Miller loops and ONE final exponentiation instead of 3 n and n.
+// ---------------------------------------------------------------------------
+struct BatchMillerArgs {
+    size_t nthreads;  // proofs
+    const G1Affine* pa;
+    const G2Affine* pb;
+    const G1Affine* pc;
+    const uint32_t* inputs;  // [n][n_inputs] plain scalars, inputs[.][0] = 1
+    uint32_t n_inputs;
+    const uint32_t* z;       // [n][4] random 128-bit coefficients
+    Fp12* f;                 // per proof: Miller value of (z A, B)
+    G1XYZZ* zc;              // per proof: z C
+    Fr* zx;                  // [n][n_inputs]: z * x_j mod r (plain)
+};
+MB_HD void batch_miller_body(const BatchMillerArgs& a, size_t tid) {
+    uint32_t k[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) k[i] = a.z[4 * tid + i];
+    G1Affine za = xyzz_to_affine(xyzz_mul(G1XYZZ::from_affine(a.pa[tid]), k));
+    G2Affine b = a.pb[tid];
+    a.f[tid] = miller_multi(&za, &b, 1);
+    a.zc[tid] = xyzz_mul(G1XYZZ::from_affine(a.pc[tid]), k);
+    Fr zf;
+    for (int i = 0; i < 8; ++i) zf.v[i] = k[i];
+    Fr zm = Fr::from_std(zf);  // Montgomery form: montmul(x, z R) = x z on plain x
+    const Fr* x = (const Fr*)(a.inputs + tid * (size_t)a.n_inputs * 8);
+    for (uint32_t j = 0; j < a.n_inputs; ++j) a.zx[tid * (size_t)a.n_inputs + j] = Fr::mul(x[j], zm);
+}
+struct BatchFinalArgs {
+    size_t nthreads;  // 1
+    size_t n;
+    const Fp12* f;
+    const G1XYZZ* zc;
+    const Fr* zx;
+    uint32_t n_inputs;
+    const G1Affine* alpha;
+    const G2Affine* beta;
+    VkDev vk;
+    uint32_t* ok;
+};
+MB_HD void batch_final_body(const BatchFinalArgs& a, size_t) {
+    Fp12 F = f12_one();
+    G1XYZZ sc = G1XYZZ::inf();
+    MB_NOUNROLL
+    for (size_t i = 0; i < a.n; ++i) {
+        F = f12_mul(F, a.f[i]);
+        xyzz_add_cold(sc, a.zc[i]);
+    }
+    // sum_j (sum_i z_i x_ij) IC_j; column 0 is sum_i z_i because x_i0 = 1
+    G1XYZZ acc = G1XYZZ::inf();
+    Fr sz = Fr::zero();
+    MB_NOUNROLL
+    for (uint32_t j = 0; j < a.n_inputs; ++j) {
+        Fr sj = Fr::zero();
+        MB_NOUNROLL
+        for (size_t i = 0; i < a.n; ++i) sj = Fr::add(sj, a.zx[i * (size_t)a.n_inputs + j]);
+        if (j == 0) sz = sj;
+        G1XYZZ t = xyzz_mul(G1XYZZ::from_affine(a.vk.ic[j]), sj.v);
+        xyzz_add_cold(acc, t);
+    }
+    G1Affine ps[3];
+    G2Affine qs[3];
+    ps[0] = xyzz_to_affine(acc);
+    qs[0] = *a.vk.gamma;
+    ps[1] = xyzz_to_affine(sc);
+    qs[1] = *a.vk.delta;
+    ps[2] = xyzz_to_affine(xyzz_mul(G1XYZZ::from_affine(*a.alpha), sz.v));
+    qs[2] = *a.beta;
+    for (int i = 0; i < 3; ++i) ps[i].y = Fp::neg(ps[i].y);
+    Fp12 f = f12_mul(F, miller_multi(ps, qs, 3));
+    *a.ok = f12_is_one(final_exponentiation(f)) ? 1u : 0u;
+}
+
 // self-test: the x-chain against the plain power, Frobenius maps against plain powers' structure
 struct PairSelfTestArgs {
     size_t nthreads;  // 1
@@ -497,11 +575,15 @@ MB_HD void pair_selftest_body(const PairSelfTestArgs& a, size_t) {
 #ifdef MB_DEFINE_PAIR
 MB_KERNEL_DEF(pair_selftest, PairSelfTestArgs, pair_selftest_body, 32)
 MB_KERNEL_DEF(proof_read, ProofReadArgs, proof_read_body, 32)
+MB_KERNEL_DEF(batch_miller, BatchMillerArgs, batch_miller_body, 32)
+MB_KERNEL_DEF(batch_final, BatchFinalArgs, batch_final_body, 32)
 MB_KERNEL_DEF(pair_prep, PairPrepArgs, pair_prep_body, 32)
 MB_KERNEL_DEF(verify_proofs, VerifyArgs, verify_body, 32)
 #else
 MB_KERNEL_DECL(pair_selftest, PairSelfTestArgs)
 MB_KERNEL_DECL(proof_read, ProofReadArgs)
+MB_KERNEL_DECL(batch_miller, BatchMillerArgs)
+MB_KERNEL_DECL(batch_final, BatchFinalArgs)
 MB_KERNEL_DECL(pair_prep, PairPrepArgs)
 MB_KERNEL_DECL(verify_proofs, VerifyArgs)
 #endif

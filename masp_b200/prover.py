@@ -260,6 +260,26 @@ def verify_proofs(params, proofs, public_inputs):
     return [b != 0 for b in ok.raw]
 
 
+def verify_proofs_batch(params, proofs, public_inputs, rng=os.urandom):
+    """One verdict for a batch of wire-form proofs (bellman's batch::Verifier / the reference's
+    BatchValidator): random 128-bit coefficients from `rng(16)` per proof, n + 3 Miller loops
+    and one final exponentiation on the device."""
+    _ensure_init()
+    n = len(proofs)
+    if n == 0:
+        return True
+    if any(len(p) != GROTH_PROOF_SIZE for p in proofs):
+        raise ValueError("a proof is %d bytes" % GROTH_PROOF_SIZE)
+    inp = b"".join((1).to_bytes(32, "little") + b"".join(int(x).to_bytes(32, "little") for x in xs)
+                   for xs in public_inputs)
+    if len(inp) != 32 * n * params.n_inputs:
+        raise ValueError("public input count does not match the verifying key")
+    z = b"".join(rng(16) for _ in range(n))
+    ok = ctypes.c_int(0)
+    check(_lib.lib().mb200_verify_proofs_batch(params._h, n, _ptr(b"".join(proofs)), _ptr(inp), _ptr(z), ctypes.byref(ok)))
+    return ok.value != 0
+
+
 def create_proof(assignment, params, r, s):
     """bellman create_proof(circuit, params, r, s) after synthesis -> 192 bytes."""
     return create_proof_batch([assignment], params, [r], [s])[0]

@@ -23,6 +23,10 @@ def uncompressed(proof_bytes):
     return G1.encode_uncompressed(a) + G2.encode_uncompressed(b) + G1.encode_uncompressed(c)
 
 
+def asg_for_batch(pv, v):
+    return pv.ProvingAssignment(H(v["a"]), H(v["b"]), H(v["c"]), H(v["inputs"]), H(v["aux"]))
+
+
 def _check(pv):
     v = GOLD
     dens = (H(v["a_aux_density"]), H(v["b_input_density"]), H(v["b_aux_density"]))
@@ -71,6 +75,14 @@ def _check(pv):
     got = pv.verify_proofs(P, [proof, bytes(flipped), bytes(off_curve), no_flag, inf_a, proof],
                            [inputs[1:]] * 5 + [wrong])
     assert got == [True, False, False, False, False, False]
+    # the randomised batch check: all-or-nothing, one final exponentiation for the batch
+    second = pv.create_proof(asg_for_batch(pv, v), P, (5).to_bytes(32, "little"), (6).to_bytes(32, "little"))
+    assert second != proof
+    assert pv.verify_proofs_batch(P, [proof, second, proof], [inputs[1:]] * 3) is True
+    assert pv.verify_proofs_batch(P, [proof, second, bytes(flipped)], [inputs[1:]] * 3) is False
+    assert pv.verify_proofs_batch(P, [proof, second], [inputs[1:], wrong]) is False
+    assert pv.verify_proofs_batch(P, [no_flag, proof], [inputs[1:]] * 2) is False
+    assert pv.verify_proofs_batch(P, [second], [inputs[1:]], rng=lambda k: b"\x01" + bytes(k - 1)) is True
     # malformed proof encodings are an error, not a verdict
     with pytest.raises(pv.Mb200Error):
         pv.verify_batch(P, [b"\xff" * 384], [inputs[1:]])
