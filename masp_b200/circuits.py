@@ -14,8 +14,8 @@ needs only the witness: `Circuit.synthesize` runs the witness half of
 Jubjub points are affine `(u, v)` integer pairs, Jubjub scalars integers.
 """
 import ctypes
-from dataclasses import dataclass, field
-from typing import List, Optional, Tuple
+from dataclasses import dataclass
+from typing import List, Tuple
 
 from . import _lib
 from ._lib import check
