@@ -147,6 +147,12 @@ int mb200_circuit_matrix(const mb200_circuit* c, int which, uint32_t* rowptr, ui
  * reference's synthesis would have returned an error for this witness. */
 int mb200_circuit_synthesize(const mb200_circuit* c, size_t n, const uint8_t* witnesses, uint8_t* inputs_out,
                              uint8_t* aux_out, int n_threads);
+/* The Pedersen hash exactly as the circuits compute it (circuit/pedersen_hash.rs:19-103 in witness
+ * form = masp_primitives::sapling::pedersen_hash): bits[0..6) are the personalization, the rest the
+ * message, one byte per bit; the result is the affine (u, v) of the hash point.  The reference's
+ * golden vectors for this function (masp_primitives/src/test_vectors/pedersen_hash_vectors.rs)
+ * pin the product's window tables, Montgomery chains and Edwards maps. */
+int mb200_pedersen_hash(const uint8_t* bits, size_t n_bits, uint8_t u_out[32], uint8_t v_out[32]);
 /* The Merkle root a Spend / Convert witness leads to (the `cur` the circuit compares with the
  * anchor, circuit/sapling.rs:343-372, convert.rs:96-124); the witness's own anchor field is ignored.
  * For callers that hold a path but not the tree (tests, benches). */

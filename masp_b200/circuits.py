@@ -109,6 +109,15 @@ class Convert:
         return _pt(vc.asset_generator) + _f(vc.value) + _f(vc.randomness) + _f(self.anchor) + _path(self.auth_path)
 
 
+def pedersen_hash(personalization_bits, bits):
+    """masp_primitives::sapling::pedersen_hash as the circuits compute it: six personalization
+    bits, then the message bits; returns the affine (u, v) of the hash point."""
+    allbits = bytes(1 if b else 0 for b in list(personalization_bits) + list(bits))
+    u, v = ctypes.create_string_buffer(32), ctypes.create_string_buffer(32)
+    check(_lib.lib().mb200_pedersen_hash(allbits, len(allbits), u, v))
+    return int.from_bytes(u.raw, "little"), int.from_bytes(v.raw, "little")
+
+
 class Circuit:
     """One recorded circuit (mb200_circuit).  Host only: needs no device."""
 

@@ -305,6 +305,24 @@ int mb200_circuit_matrix(const mb200_circuit* c, int which, uint32_t* rowptr, ui
     return MB200_OK;
 }
 
+int mb200_pedersen_hash(const uint8_t* bits, size_t n_bits, uint8_t u_out[32], uint8_t v_out[32]) {
+    if (!bits || !u_out || !v_out || n_bits < 6 || n_bits > 6 + 3 * 63 * 6) return MB200_EINVAL;
+    try {
+        CS cs;
+        bool pers[6];
+        for (int i = 0; i < 6; ++i) pers[i] = bits[i] != 0;
+        Bits in;
+        for (size_t i = 6; i < n_bits; ++i) in.push_back(Boolean::from_bit(AllocatedBit::alloc(cs, bits[i] != 0)));
+        EdwardsPoint h = pedersen_hash(cs, pers, in);
+        if (cs.failed) return MB200_ESYNTH;
+        h.u.value.to_bytes(u_out);
+        h.v.value.to_bytes(v_out);
+    } catch (const std::bad_alloc&) {
+        return MB200_ENOMEM;
+    }
+    return MB200_OK;
+}
+
 int mb200_circuit_root(const mb200_circuit* c, const uint8_t* witness, uint8_t root_out[32]) {
     if (!c || !witness || !root_out || c->kind == MB200_CIRCUIT_OUTPUT) return MB200_EINVAL;
     try {
