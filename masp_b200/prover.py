@@ -12,8 +12,10 @@ Witness synthesis (Circuit::synthesize into bellman's ProvingAssignment) is
 above this path (NEXT-1): the *_proof methods take the
 ProvingAssignment a Rust caller would hand to the FFI -- the per-row
 evaluations a, b, c, the input and aux assignments -- plus, at key load, the
-three density bitmaps.  jubjub-side bookkeeping of SaplingProvingContext
-(bsk, cv_sum, binding_sig) is not Groth16 work and stays with the caller.
+three density bitmaps -- or, for keys loaded with the library's own circuits
+bound, the circuit instance itself.  The callers' side of those methods
+(SaplingProvingContext: bsk, cv_sum, binding_sig, and the TxProver trait with
+the wallet-level argument lists) is masp_b200/sapling.py.
 """
 import ctypes
 import hashlib
@@ -438,6 +440,12 @@ class LocalTxProver:
             else:
                 res.append(create_proof_batch(group, params, [p[0] for p in pairs], [p[1] for p in pairs]))
         return tuple(res)
+
+    def tx_prover(self, batching=False):
+        """`impl TxProver for LocalTxProver` (masp_proofs/src/prover.rs:156-261): the trait object over
+        these keys; batching=True defers every proof of a transaction to one launch per circuit."""
+        from . import sapling
+        return (sapling.BatchingTxProver if batching else sapling.TxProver)(self)
 
 
 # ---------------------------------------------------------------------------
