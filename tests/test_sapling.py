@@ -287,14 +287,33 @@ def test_v5_sapling_bundle_layout_round_trip():
 # ---------------------------------------------------------------------------
 # the whole surface on the device
 # ---------------------------------------------------------------------------
+def _real_key(name):
+    """Key of a real MASP circuit under a known trapdoor (test_circuits.real_instance: the oracle's setup over
+    the oracle's recording of the circuit).  Generating the three takes about a minute of CPU, so the bytes are
+    cached under tests/_cache (git-ignored; it travels to the GPU box with the snapshot when present)."""
+    cache = os.path.join(os.path.dirname(__file__), "_cache")
+    path = os.path.join(cache, "key_%s.bin" % name)
+    if os.path.exists(path):
+        return open(path, "rb").read()
+    from test_circuits import real_instance
+    key = real_instance(name)[1]
+    try:
+        os.makedirs(cache, exist_ok=True)
+        with open(path + ".tmp", "wb") as f:
+            f.write(key)
+        os.replace(path + ".tmp", path)
+    except OSError:
+        pass
+    return key
+
+
 @pytest.mark.gpu
 def test_tx_prover_end_to_end_gpu(gpu):
     """One shielded transaction through the TxProver trait, serial and batched: every proof is accepted by
     verify_proof under NATIVELY computed public inputs (the device pairing check inside spend_proof /
     convert_proof, and again here including the Output proofs the reference does not self-check), a
     tampered public input is rejected, and the binding signature verifies against the accumulated bvk."""
-    from test_circuits import real_instance
-    keys = {n: real_instance(n)[1] for n in ("spend", "output", "convert")}   # trusted setups with known trapdoors
+    keys = {n: _real_key(n) for n in ("spend", "output", "convert")}   # trusted setups with known trapdoors
     local = gpu.LocalTxProver.from_bytes(keys["spend"], keys["output"], keys["convert"], verify_hashes=False)
     nam, epoch1 = S.AssetType.new(b"NAM"), S.AssetType.new(b"NAM/epoch1")
     conv = S.AllowedConversion({nam: -1, epoch1: 1})
