@@ -284,6 +284,58 @@ MB_K_MSM_G1(msm_accumulate_g1, AccArgs<Fp>, acc_g1_body, 128)
 // profiles/r01_acc_128reg_ab.jsonl)
 MB_K_MSM_G2(msm_accumulate_g2, AccArgs<Fp2>, acc_g2_body, 64)
 
+// Lock-step variant (opt-in, MB200_ACC_LOCKSTEP=1: G1, =2: G1 and G2; not yet measured on a B200).
+// Why: in the profile of msm_accumulate_g1 the second-largest stall after the IMAD dependency `wait`
+// is `no_instructions` (16 % of the samples): the loop body is ~72 KB of straight-line code and the
+// 12 resident warps of an SM sit at 12 different places in it, so every warp streams the whole body
+// through the instruction caches on its own.  Here ONE block fills the SM (384 threads at 166
+// registers; 256 at 255 for G2) and a barrier closes every iteration, so the three (two) warps of a
+// scheduler fetch the same lines at the same time.  The barrier doubles as the loop condition
+// (`__syncthreads_or`): tasks are handed out longest first, so the trip counts inside a block differ
+// by a few iterations at most.  Results are identical: same additions in the same order per task.
+#if !defined(MB200_EMU) && (defined(MB_DEFINE_MSM_G1) || defined(MB_DEFINE_MSM_G2))
+template <class F, int BLOCK>
+__device__ __forceinline__ void acc_lockstep_body(const AccArgs<F>& a) {
+    const size_t tid = (size_t)blockIdx.x * BLOCK + threadIdx.x;
+    const bool live = tid < *a.ntasks;
+    const uint32_t t = live ? a.order[tid] : 0;
+    const uint32_t n = live ? a.task_len[t] : 0;
+    const uint32_t* e = a.entries + (live ? a.task_start[t] : 0);
+    XYZZ<F> acc = XYZZ<F>::inf();
+    MB_NOUNROLL
+    for (uint32_t i = 0; __syncthreads_or(i < n); ++i) {
+        if (i < n) {
+            uint32_t ent = e[i];
+            Affine<F> q = a.table[ent >> 1];
+            xyzz_madd(acc, q, (ent & 1) != 0);
+        }
+    }
+    if (live) a.partials[t] = acc;
+}
+#endif
+#if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G1)
+__global__ void __launch_bounds__(384, 1) msm_accumulate_g1_lockstep(const AccArgs<Fp> a) { acc_lockstep_body<Fp, 384>(a); }
+void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s) {
+    if (!a.nthreads) return;
+    msm_accumulate_g1_lockstep<<<(unsigned)((a.nthreads + 383) / 384), 384, 0, s>>>(a);
+    MB_CUDA(cudaGetLastError());
+    ::mb::g_launches++;
+}
+#else
+void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s);
+#endif
+#if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G2)
+__global__ void __launch_bounds__(256, 1) msm_accumulate_g2_lockstep(const AccArgs<Fp2> a) { acc_lockstep_body<Fp2, 256>(a); }
+void launch_msm_accumulate_g2_lockstep(const AccArgs<Fp2>& a, cudaStream_t s) {
+    if (!a.nthreads) return;
+    msm_accumulate_g2_lockstep<<<(unsigned)((a.nthreads + 255) / 256), 256, 0, s>>>(a);
+    MB_CUDA(cudaGetLastError());
+    ::mb::g_launches++;
+}
+#else
+void launch_msm_accumulate_g2_lockstep(const AccArgs<Fp2>& a, cudaStream_t s);
+#endif
+
 // bucket sum = sum of its segments' partial sums (one for almost every bucket)
 template <class F>
 struct CombineArgs {
@@ -422,10 +474,31 @@ inline uint32_t red_log_t(const char* name, uint32_t dflt) {
 
 template <class F>
 inline void launch_acc(const AccArgs<F>& a, cudaStream_t s);
+inline uint32_t msm_acc_lockstep() {
+#ifdef MB200_EMU
+    return 0;  // a barrier has no host counterpart; the variant adds no arithmetic of its own
+#else
+    static const uint32_t v = [] {
+        const char* e = getenv("MB200_ACC_LOCKSTEP");
+        return (e && *e) ? (uint32_t)strtoul(e, nullptr, 10) : 0u;
+    }();
+    return v;
+#endif
+}
 template <>
-inline void launch_acc<Fp>(const AccArgs<Fp>& a, cudaStream_t s) { launch_msm_accumulate_g1(a, s); }
+inline void launch_acc<Fp>(const AccArgs<Fp>& a, cudaStream_t s) {
+#ifndef MB200_EMU
+    if (msm_acc_lockstep() >= 1 && !a.direct) return launch_msm_accumulate_g1_lockstep(a, s);
+#endif
+    launch_msm_accumulate_g1(a, s);
+}
 template <>
-inline void launch_acc<Fp2>(const AccArgs<Fp2>& a, cudaStream_t s) { launch_msm_accumulate_g2(a, s); }
+inline void launch_acc<Fp2>(const AccArgs<Fp2>& a, cudaStream_t s) {
+#ifndef MB200_EMU
+    if (msm_acc_lockstep() >= 2 && !a.direct) return launch_msm_accumulate_g2_lockstep(a, s);
+#endif
+    launch_msm_accumulate_g2(a, s);
+}
 template <class F>
 inline void launch_combine(const CombineArgs<F>& a, cudaStream_t s);
 template <>

@@ -217,6 +217,10 @@ struct NttPlan {
     bool inverse = false;
 };
 
+}  // namespace mb
+#include "ntt_smem.cuh"
+namespace mb {
+
 // One transform of `batch` items: src -> dst through the two scratch buffers
 // (each batch * n elements, stride n).  src / dst strides are free.
 inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const Fr* src, size_t src_stride, Fr* dst,
@@ -228,6 +232,45 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
         uint32_t k = v && *v ? (uint32_t)strtoul(v, nullptr, 10) : 3;
         return k < 1 ? 1u : (k > 3 ? 3u : k);
     }();
+    if (ntt_smem_mode() != 0 && ntt_smem_supported(d.log_n)) {
+        // opt-in: two shared-memory kernels (ntt_smem.cuh) instead of the pass loop below
+        NttFusedArgs f;
+        f.log_n = d.log_n;
+        f.inverse = p.inverse ? 1 : 0;
+        f.tw = d.tw.as<Fr>();
+        f.k1 = d.k1;
+        f.k2 = d.k2;
+        f.bulk_store = ntt_smem_mode() >= 2 ? 1 : 0;
+        f.group = 0;
+        f.L = NTT_SMEM_L1;
+        f.logC = 11 - f.L;
+        f.nblocks = (size_t)batch * ((n >> f.L) >> f.logC);
+        f.src = src;
+        f.src_stride = src_stride;
+        f.dst = tmp0;
+        f.dst_stride = n;
+        f.src_len = p.src_len ? p.src_len : n;
+        f.in_scale = p.in_scale;
+        f.srcb = p.srcb;
+        f.srcc = p.srcc;
+        f.out_scale = nullptr;
+        launch_ntt_fused(f, s);
+        f.group = 1;
+        f.L = d.log_n - NTT_SMEM_L1;
+        f.logC = 11 - f.L;
+        f.nblocks = (size_t)batch * ((n >> f.L) >> f.logC);
+        f.src = tmp0;
+        f.src_stride = n;
+        f.dst = dst;
+        f.dst_stride = dst_stride;
+        f.src_len = n;
+        f.in_scale = nullptr;
+        f.srcb = nullptr;
+        f.srcc = nullptr;
+        f.out_scale = p.out_scale;
+        launch_ntt_fused(f, s);
+        return;
+    }
     const Fr* cur = src;
     size_t cur_stride = src_stride;
     int flip = 0;

@@ -129,6 +129,56 @@ def test_pair_rounds_variant():
     assert r.returncode == 0, r.stdout[-2000:]
 
 
+_NTT_SMEM_CHILD = r"""
+import hashlib, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from util import load_emu, ib, rand_scalars
+emu = load_emu()
+for log_n in (11, 12, 16, 17):
+    v = ib(rand_scalars(1 << log_n, log_n, "uniform"))
+    for inv in (False, True):
+        for cos in (False, True):
+            l0 = emu.get_counter("launches")
+            out = emu.ntt(v, log_n, inv, cos)
+            print("ntt", log_n, int(inv), int(cos), hashlib.sha256(out).hexdigest(), "launches", int(emu.get_counter("launches") - l0))
+for rows in (2049, 31211):
+    a, b = ib(rand_scalars(rows, 1, "uniform")), ib(rand_scalars(rows, 2, "uniform"))
+    c = emu.fr_mul(a, b, rows)
+    print("h", rows, hashlib.sha256(emu.h_coeffs(a, b, c, rows)).hexdigest())
+"""
+
+
+@pytest.mark.slow
+def test_ntt_shared_memory_variant():
+    """The opt-in two-kernel shared-memory NTT (csrc/ntt_smem.cuh, MB200_NTT_SMEM=1) against the
+    pass-per-launch path: same bytes for every mode (forward / inverse, coset or not) at sizes on both
+    sides of its range (2^12 .. 2^18), and through the fused H pipeline (2^12 and the Output size 2^15) -- and it really is two launches where the default path needs four to six."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runs = {}
+    procs = {mode: subprocess.Popen([sys.executable, "-c", _NTT_SMEM_CHILD, root],
+                                    env=dict(os.environ, MB200_NTT_SMEM=mode), stdout=subprocess.PIPE,
+                                    stderr=subprocess.PIPE, text=True) for mode in ("0", "1")}
+    for mode, pr in procs.items():
+        out, err = pr.communicate(timeout=900)
+        assert pr.returncode == 0, err[-2000:]
+        runs[mode] = [l.split() for l in out.strip().splitlines()]
+    assert len(runs["0"]) == len(runs["1"]) == 4 * 4 + 2
+    for base, smem in zip(runs["0"], runs["1"]):
+        if base[0] == "h":
+            assert base == smem
+            continue
+        assert base[:5] == smem[:5], base[:4]          # same digest
+        log_n = int(base[1])
+        # the coset modes add a scaling launch in front / behind; the transform itself:
+        if 12 <= log_n <= 18:
+            assert int(base[-1]) - int(smem[-1]) == (log_n + 2) // 3 - 2, (base, smem)
+        else:
+            assert base[-1] == smem[-1]
+
+
 @pytest.mark.slow
 def test_extreme_r_s(emu, oracle):
     """r and s at the ends of the range: the GLV split of the two scalar multiplications in C
