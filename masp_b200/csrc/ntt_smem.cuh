@@ -18,7 +18,7 @@
 //                       memory and scatters with the same pattern.
 //
 // Global traffic per transform drops from 6 reads + 6 writes of the polynomial to 2 + 2.  A
-// block is 256 threads on 64 KB of shared memory (2048 scalars); every pass is "each thread
+// block is 256 threads on 72 KB of shared memory (2048 scalars plus one pad scalar per array); every pass is "each thread
 // reads its 8 values, barrier, each thread writes its 8 results, barrier", so one buffer serves
 // in place.  The fused scalings of ntt.cuh keep their places: zero padding / coset scale /
 // (a b - c) / Z on the loads of kernel 1, the output scale on the stores of kernel 2.
@@ -44,6 +44,9 @@ struct NttFusedArgs {
 };
 
 static const uint32_t NTT_SMEM_ELEMS = 2048, NTT_SMEM_THREADS = 256, NTT_SMEM_L1 = 9;
+// arrays sit Ln + 1 elements apart: consecutive arrays start 8 banks apart, so the gather / scatter phases
+// (consecutive threads -> consecutive arrays) do not pile onto one bank group; at most 2048 / 8 arrays
+static const uint32_t NTT_SMEM_ALLOC = NTT_SMEM_ELEMS + NTT_SMEM_ELEMS / 8;
 
 #ifdef MB200_EMU
 #define MB_FOR_THREADS(t) for (uint32_t t = 0; t < NTT_SMEM_THREADS; ++t)
@@ -102,7 +105,7 @@ template <int K>
 MB_BLOCK_FN void ntt_fused_pass(const NttFusedArgs& a, Fr* sm, Fr (*regs)[8], uint32_t g0, uint32_t ns_loc) {
     constexpr int R = 1 << K;
     constexpr int ITEMS = 8 / R;               // work items per thread
-    const uint32_t Ln = 1u << a.L, per = Ln >> K, S = 1u << (a.log_n - a.L);
+    const uint32_t Ln = 1u << a.L, Lp = Ln + 1, per = Ln >> K, S = 1u << (a.log_n - a.L);
     MB_FOR_THREADS(t) {
         Fr* v = regs[MB_TSLOT(t)];
         MB_UNROLL
@@ -110,7 +113,7 @@ MB_BLOCK_FN void ntt_fused_pass(const NttFusedArgs& a, Fr* sm, Fr (*regs)[8], ui
             uint32_t w = t + (uint32_t)it * NTT_SMEM_THREADS;
             uint32_t c = w / per, j = w - c * per;
             MB_UNROLL
-            for (int r = 0; r < R; ++r) v[it * R + r] = sm[c * Ln + j + (uint32_t)r * per];
+            for (int r = 0; r < R; ++r) v[it * R + r] = sm[c * Lp + j + (uint32_t)r * per];
         }
     }
     MB_BLOCK_SYNC();
@@ -130,7 +133,7 @@ MB_BLOCK_FN void ntt_fused_pass(const NttFusedArgs& a, Fr* sm, Fr (*regs)[8], ui
                 int q = 0;
                 MB_UNROLL
                 for (int b = 0; b < K; ++b) q |= ((i >> b) & 1) << (K - 1 - b);
-                sm[c * Ln + j0 + (uint32_t)q * ns_loc] = v[it * R + i];
+                sm[c * Lp + j0 + (uint32_t)q * ns_loc] = v[it * R + i];
             }
         }
     }
@@ -138,7 +141,7 @@ MB_BLOCK_FN void ntt_fused_pass(const NttFusedArgs& a, Fr* sm, Fr (*regs)[8], ui
 }
 
 MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (*regs)[8]) {
-    const uint32_t n = 1u << a.log_n, Ln = 1u << a.L, C = 1u << a.logC, S = n >> a.L;
+    const uint32_t n = 1u << a.log_n, Ln = 1u << a.L, Lp = Ln + 1, C = 1u << a.logC, S = n >> a.L;
     const uint32_t blocks_per_item = S >> a.logC;
     const size_t item = blk / blocks_per_item;
     const uint32_t g0 = (uint32_t)(blk - item * blocks_per_item) << a.logC;
@@ -161,7 +164,7 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
                 }
                 if (a.in_scale) x = Fr::mul(x, a.in_scale[idx]);
             }
-            sm[c * Ln + s] = x;
+            sm[c * Lp + s] = x;
         }
     }
     MB_BLOCK_SYNC();
@@ -184,7 +187,7 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
             if (threadIdx.x == 0) {
                 MB_NOUNROLL
                 for (uint32_t c = 0; c < C; ++c) {
-                    uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sm + c * Ln);
+                    uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sm + c * Lp);
                     Fr* gptr = dst + (size_t)(g0 + c) * Ln;
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr),
                                  "r"(saddr), "r"(Ln * (uint32_t)sizeof(Fr))
@@ -201,7 +204,7 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
             for (int i = 0; i < 8; ++i) {
                 uint32_t e = t + (uint32_t)i * NTT_SMEM_THREADS;
                 uint32_t c = e >> a.L, k = e & (Ln - 1);
-                dst[(size_t)(g0 + c) * Ln + k] = sm[c * Ln + k];
+                dst[(size_t)(g0 + c) * Ln + k] = sm[c * Lp + k];
             }
         }
     } else {
@@ -211,7 +214,7 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
                 uint32_t e = t + (uint32_t)i * NTT_SMEM_THREADS;
                 uint32_t c = e & (C - 1), o = e >> a.logC;
                 uint32_t idx = g0 + c + o * S;
-                Fr val = sm[c * Ln + o];
+                Fr val = sm[c * Lp + o];
                 if (a.out_scale) val = Fr::mul(val, a.out_scale[idx]);
                 dst[idx] = val;
             }
@@ -222,7 +225,7 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
 #ifdef MB200_EMU
 #ifdef MB_DEFINE_NTT
 void launch_ntt_fused(const NttFusedArgs& a, cudaStream_t) {
-    Fr* sm = new Fr[NTT_SMEM_ELEMS];
+    Fr* sm = new Fr[NTT_SMEM_ALLOC];
     Fr(*regs)[8] = new Fr[NTT_SMEM_THREADS][8];
     for (size_t b = 0; b < a.nblocks; ++b) ntt_fused_block(a, b, sm, regs);
     delete[] sm;
@@ -243,11 +246,11 @@ void launch_ntt_fused(const NttFusedArgs& a, cudaStream_t s) {
     if (!a.nblocks) return;
     static const bool attr = [] {
         MB_CUDA(cudaFuncSetAttribute(ntt_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(NTT_SMEM_ELEMS * sizeof(Fr))));
+                                     (int)(NTT_SMEM_ALLOC * sizeof(Fr))));
         return true;
     }();
     (void)attr;
-    ntt_fused<<<(unsigned)a.nblocks, NTT_SMEM_THREADS, NTT_SMEM_ELEMS * sizeof(Fr), s>>>(a);
+    ntt_fused<<<(unsigned)a.nblocks, NTT_SMEM_THREADS, NTT_SMEM_ALLOC * sizeof(Fr), s>>>(a);
     MB_CUDA(cudaGetLastError());
     ::mb::g_launches++;
 }
