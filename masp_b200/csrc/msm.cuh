@@ -284,7 +284,8 @@ MB_K_MSM_G1(msm_accumulate_g1, AccArgs<Fp>, acc_g1_body, 128)
 // profiles/r01_acc_128reg_ab.jsonl)
 MB_K_MSM_G2(msm_accumulate_g2, AccArgs<Fp2>, acc_g2_body, 64)
 
-// Lock-step variant (opt-in, MB200_ACC_LOCKSTEP=1: G1, =2: G1 and G2; not yet measured on a B200).
+// Lock-step variant (opt-in, MB200_ACC_LOCKSTEP=1: G1, =2: G1 and G2, =3: G1 with an L2 prefetch of the
+// next table point; not yet measured on a B200).
 // Why: in the profile of msm_accumulate_g1 the second-largest stall after the IMAD dependency `wait`
 // is `no_instructions` (16 % of the samples): the loop body is ~72 KB of straight-line code and the
 // 12 resident warps of an SM sit at 12 different places in it, so every warp streams the whole body
@@ -294,7 +295,7 @@ MB_K_MSM_G2(msm_accumulate_g2, AccArgs<Fp2>, acc_g2_body, 64)
 // (`__syncthreads_or`): tasks are handed out longest first, so the trip counts inside a block differ
 // by a few iterations at most.  Results are identical: same additions in the same order per task.
 #if !defined(MB200_EMU) && (defined(MB_DEFINE_MSM_G1) || defined(MB_DEFINE_MSM_G2))
-template <class F, int BLOCK>
+template <class F, int BLOCK, bool PREFETCH>
 __device__ __forceinline__ void acc_lockstep_body(const AccArgs<F>& a) {
     const size_t tid = (size_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool live = tid < *a.ntasks;
@@ -302,10 +303,19 @@ __device__ __forceinline__ void acc_lockstep_body(const AccArgs<F>& a) {
     const uint32_t n = live ? a.task_len[t] : 0;
     const uint32_t* e = a.entries + (live ? a.task_start[t] : 0);
     XYZZ<F> acc = XYZZ<F>::inf();
+    uint32_t nxt = n ? e[0] : 0;
     MB_NOUNROLL
     for (uint32_t i = 0; __syncthreads_or(i < n); ++i) {
         if (i < n) {
-            uint32_t ent = e[i];
+            uint32_t ent = nxt;
+            if (i + 1 < n) {
+                nxt = e[i + 1];
+                if (PREFETCH) {  // level 3: pull the next table point towards L2 while this addition runs
+                    const char* nq = reinterpret_cast<const char*>(a.table + (nxt >> 1));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nq));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + sizeof(Affine<F>) - 1));
+                }
+            }
             Affine<F> q = a.table[ent >> 1];
             xyzz_madd(acc, q, (ent & 1) != 0);
         }
@@ -314,18 +324,25 @@ __device__ __forceinline__ void acc_lockstep_body(const AccArgs<F>& a) {
 }
 #endif
 #if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G1)
-__global__ void __launch_bounds__(384, 1) msm_accumulate_g1_lockstep(const AccArgs<Fp> a) { acc_lockstep_body<Fp, 384>(a); }
-void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s) {
+__global__ void __launch_bounds__(384, 1) msm_accumulate_g1_lockstep(const AccArgs<Fp> a) {
+    acc_lockstep_body<Fp, 384, false>(a);
+}
+__global__ void __launch_bounds__(384, 1) msm_accumulate_g1_lockstep_pf(const AccArgs<Fp> a) {
+    acc_lockstep_body<Fp, 384, true>(a);
+}
+void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s, bool prefetch) {
     if (!a.nthreads) return;
-    msm_accumulate_g1_lockstep<<<(unsigned)((a.nthreads + 383) / 384), 384, 0, s>>>(a);
+    const unsigned grid = (unsigned)((a.nthreads + 383) / 384);
+    if (prefetch) msm_accumulate_g1_lockstep_pf<<<grid, 384, 0, s>>>(a);
+    else msm_accumulate_g1_lockstep<<<grid, 384, 0, s>>>(a);
     MB_CUDA(cudaGetLastError());
     ::mb::g_launches++;
 }
 #else
-void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s);
+void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s, bool prefetch);
 #endif
 #if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G2)
-__global__ void __launch_bounds__(256, 1) msm_accumulate_g2_lockstep(const AccArgs<Fp2> a) { acc_lockstep_body<Fp2, 256>(a); }
+__global__ void __launch_bounds__(256, 1) msm_accumulate_g2_lockstep(const AccArgs<Fp2> a) { acc_lockstep_body<Fp2, 256, false>(a); }
 void launch_msm_accumulate_g2_lockstep(const AccArgs<Fp2>& a, cudaStream_t s) {
     if (!a.nthreads) return;
     msm_accumulate_g2_lockstep<<<(unsigned)((a.nthreads + 255) / 256), 256, 0, s>>>(a);
@@ -488,14 +505,14 @@ inline uint32_t msm_acc_lockstep() {
 template <>
 inline void launch_acc<Fp>(const AccArgs<Fp>& a, cudaStream_t s) {
 #ifndef MB200_EMU
-    if (msm_acc_lockstep() >= 1 && !a.direct) return launch_msm_accumulate_g1_lockstep(a, s);
+    if (msm_acc_lockstep() >= 1 && !a.direct) return launch_msm_accumulate_g1_lockstep(a, s, msm_acc_lockstep() == 3);
 #endif
     launch_msm_accumulate_g1(a, s);
 }
 template <>
 inline void launch_acc<Fp2>(const AccArgs<Fp2>& a, cudaStream_t s) {
 #ifndef MB200_EMU
-    if (msm_acc_lockstep() >= 2 && !a.direct) return launch_msm_accumulate_g2_lockstep(a, s);
+    if (msm_acc_lockstep() == 2 && !a.direct) return launch_msm_accumulate_g2_lockstep(a, s);
 #endif
     launch_msm_accumulate_g2(a, s);
 }
