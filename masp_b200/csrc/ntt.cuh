@@ -215,6 +215,10 @@ struct NttPlan {
     const Fr* srcc = nullptr;
     uint32_t src_len = 0;  // 0 = n
     bool inverse = false;
+    // shared-memory path only (ntt_smem.cuh): after out_scale, val = (val - sub[o] * sub_k) * post_k
+    const Fr* sub = nullptr;
+    size_t sub_stride = 0;
+    Fr sub_k, post_k;
 };
 
 }  // namespace mb
@@ -240,7 +244,10 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
         f.tw = d.tw.as<Fr>();
         f.k1 = d.k1;
         f.k2 = d.k2;
-        f.bulk_store = ntt_smem_mode() >= 2 ? 1 : 0;
+        f.bulk_store = (ntt_smem_mode() & 2) ? 1 : 0;
+        f.sub = nullptr;
+        f.sub_stride = 0;
+        f.k3 = d.k2;
         f.group = 0;
         f.L = NTT_SMEM_L1;
         f.logC = 11 - f.L;
@@ -268,6 +275,12 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
         f.srcb = nullptr;
         f.srcc = nullptr;
         f.out_scale = p.out_scale;
+        if (p.sub) {
+            f.sub = p.sub;
+            f.sub_stride = p.sub_stride;
+            f.k3 = p.sub_k;
+            f.k2 = p.post_k;
+        }
         launch_ntt_fused(f, s);
         return;
     }
@@ -320,6 +333,28 @@ inline void h_pipeline(const NttDomain& d, uint32_t batch, uint32_t rows, const 
     p1.inverse = true;
     p1.src_len = rows;
     ntt_run(d, p1, batch * 3, abc, poly_stride, work2, n, work0, work1, s);
+    if ((ntt_smem_mode() & 4) && ntt_smem_supported(d.log_n)) {
+        // Opt-in: SIX transforms.  The inverse coset transform is linear, so
+        //   icoset[(a b - c)(g w^i) / (g^m - 1)] = (icoset[(a b)(g w^i)] - c(X)) / (g^m - 1)
+        // coefficient by coefficient, and c(X) is already there after step 1: the coset transform
+        // of c is never needed.  Same field elements as the seven-transform form for ANY rows
+        // (satisfied or not), hence the same proof bytes.
+        NttPlan q2;
+        q2.in_scale = d.cos_fwd.as<Fr>();
+        for (uint32_t poly = 0; poly < 2; ++poly)   // a and b only; polynomials of a proof sit n apart
+            ntt_run(d, q2, batch, work2 + (size_t)poly * n, 3 * (size_t)n, work3 + (size_t)poly * n, 3 * (size_t)n, work0,
+                    work1, s);
+        NttPlan q3;
+        q3.inverse = true;
+        q3.srcb = work3 + n;            // plain product a * b on load
+        q3.out_scale = d.cos_inv.as<Fr>();   // g^-i / m
+        q3.sub = work2 + 2 * (size_t)n;      // raw inverse transform of c: still lacks its 1/m
+        q3.sub_stride = 3 * (size_t)n;
+        q3.sub_k = d.minv;
+        q3.post_k = d.k2;               // 1 / (g^m - 1), Montgomery form
+        ntt_run(d, q3, batch, work3, 3 * (size_t)n, hout, hout_stride, work0, work1, s);
+        return;
+    }
     // 2. coset forward transforms; 1/m and g^i folded into the load
     NttPlan p2;
     p2.in_scale = d.cos_fwd.as<Fr>();

@@ -1,6 +1,6 @@
 // Shared-memory formulation of the Stockham NTT: two kernels instead of six passes.
 //
-// OPT-IN (MB200_NTT_SMEM=1, =2 adds the TMA bulk store); bit-identical to the pass-per-launch
+// OPT-IN (MB200_NTT_SMEM=1, =2 adds the TMA bulk store, =5 / =7 the six-transform H pipeline); bit-identical to the pass-per-launch
 // path of ntt.cuh (tests/test_emu.py runs both), not yet measured on a B200 -- see DESIGN.md §4.1.
 //
 // The first three radix-8 passes of the autosort transform of size n are, for every residue
@@ -39,8 +39,11 @@ struct NttFusedArgs {
     const Fr* in_scale;
     const Fr* out_scale;
     const Fr* srcb;
-    const Fr* srcc;
+    const Fr* srcc;       // nullptr with srcb set: plain product a * b on load
     Fr k1, k2;
+    const Fr* sub;        // optional, group 1 store: val = (val - sub[idx] * k3) * k2
+    size_t sub_stride;
+    Fr k3;
 };
 
 static const uint32_t NTT_SMEM_ELEMS = 2048, NTT_SMEM_THREADS = 256, NTT_SMEM_L1 = 9;
@@ -159,8 +162,12 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
                 x = src[idx];
                 if (a.srcb) {
                     Fr b = a.srcb[item * a.src_stride + idx];
-                    Fr cc = a.srcc[item * a.src_stride + idx];
-                    x = Fr::sub(Fr::mul(Fr::mul(x, b), a.k1), Fr::mul(cc, a.k2));
+                    if (a.srcc) {
+                        Fr cc = a.srcc[item * a.src_stride + idx];
+                        x = Fr::sub(Fr::mul(Fr::mul(x, b), a.k1), Fr::mul(cc, a.k2));
+                    } else {
+                        x = Fr::mul(Fr::mul(x, b), Fr::r2());
+                    }
                 }
                 if (a.in_scale) x = Fr::mul(x, a.in_scale[idx]);
             }
@@ -216,6 +223,7 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
                 uint32_t idx = g0 + c + o * S;
                 Fr val = sm[c * Lp + o];
                 if (a.out_scale) val = Fr::mul(val, a.out_scale[idx]);
+                if (a.sub) val = Fr::mul(Fr::sub(val, Fr::mul(a.sub[item * a.sub_stride + idx], a.k3)), a.k2);
                 dst[idx] = val;
             }
         }
@@ -259,11 +267,15 @@ void launch_ntt_fused(const NttFusedArgs& a, cudaStream_t s);
 #endif
 #endif
 
-// 0: pass-per-launch path (default); 1: shared-memory kernels; 2: with the TMA bulk store
+// 0: pass-per-launch path (default).  Bit 0: shared-memory kernels; value 2 or bit 1 with bit 0: TMA bulk
+// store in kernel 1; bit 2 (with bit 0): the H pipeline with six transforms instead of seven (ntt.cuh).
+// So 1 = smem, 2 or 3 = smem + TMA, 5 = smem + six transforms, 7 = all three.
 inline uint32_t ntt_smem_mode() {
     static const uint32_t v = [] {
         const char* e = getenv("MB200_NTT_SMEM");
-        return (e && *e) ? (uint32_t)strtoul(e, nullptr, 10) : 0u;
+        uint32_t m = (e && *e) ? (uint32_t)strtoul(e, nullptr, 10) : 0u;
+        if (m == 2) m = 3;
+        return (m & 1) ? m : 0u;
     }();
     return v;
 }

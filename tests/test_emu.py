@@ -145,6 +145,8 @@ for rows in (2049, 31211):
     a, b = ib(rand_scalars(rows, 1, "uniform")), ib(rand_scalars(rows, 2, "uniform"))
     c = emu.fr_mul(a, b, rows)
     print("h", rows, hashlib.sha256(emu.h_coeffs(a, b, c, rows)).hexdigest())
+    c = ib(rand_scalars(rows, 3))      # unsatisfied rows: the division by Z is not exact
+    print("h", -rows, hashlib.sha256(emu.h_coeffs(a, b, c, rows)).hexdigest())
 """
 
 
@@ -152,7 +154,8 @@ for rows in (2049, 31211):
 def test_ntt_shared_memory_variant():
     """The opt-in two-kernel shared-memory NTT (csrc/ntt_smem.cuh, MB200_NTT_SMEM=1) against the
     pass-per-launch path: same bytes for every mode (forward / inverse, coset or not) at sizes on both
-    sides of its range (2^12 .. 2^18), and through the fused H pipeline (2^12 and the Output size 2^15) -- and it really is two launches where the default path needs four to six."""
+    sides of its range (2^12 .. 2^18), and through the fused H pipeline (2^12 and the Output size 2^15,
+    satisfied and unsatisfied rows, with seven transforms and with six) -- and it really is two launches where the default path needs four to six."""
     import os
     import subprocess
     import sys
@@ -160,12 +163,15 @@ def test_ntt_shared_memory_variant():
     runs = {}
     procs = {mode: subprocess.Popen([sys.executable, "-c", _NTT_SMEM_CHILD, root],
                                     env=dict(os.environ, MB200_NTT_SMEM=mode), stdout=subprocess.PIPE,
-                                    stderr=subprocess.PIPE, text=True) for mode in ("0", "1")}
+                                    stderr=subprocess.PIPE, text=True) for mode in ("0", "1", "5")}
     for mode, pr in procs.items():
         out, err = pr.communicate(timeout=900)
         assert pr.returncode == 0, err[-2000:]
         runs[mode] = [l.split() for l in out.strip().splitlines()]
-    assert len(runs["0"]) == len(runs["1"]) == 4 * 4 + 2
+    assert len(runs["0"]) == len(runs["1"]) == len(runs["5"]) == 4 * 4 + 4
+    # mode 5: the H pipeline with six transforms (the coset transform of c is never needed because the
+    # inverse coset transform is linear): same coefficients for satisfied AND unsatisfied rows
+    assert [l for l in runs["5"] if l[0] == "h"] == [l for l in runs["0"] if l[0] == "h"]
     for base, smem in zip(runs["0"], runs["1"]):
         if base[0] == "h":
             assert base == smem

@@ -9,7 +9,8 @@ shipped path is judged by.  scripts/gpu_r2_variants.sh runs these and the A/B be
                             (instruction-cache locality), G1 or G1 + G2; 3 = G1 with an L2 prefetch of the next table point.
   * MB200_NTT_SMEM=1|2      csrc/ntt_smem.cuh: the Stockham transform as two shared-memory kernels
                             (2 global passes instead of 6); =2 stores kernel 1's contiguous runs with
-                            TMA bulk copies (cp.async.bulk.global.shared::cta).
+                            TMA bulk copies (cp.async.bulk.global.shared::cta); =5 / =7 run the H pipeline with six
+                            transforms instead of seven.
 """
 import os
 import subprocess
@@ -40,6 +41,6 @@ def test_accumulate_lockstep_variant_gpu(level):
 
 @enabled
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1", "2", "5", "7"])
 def test_ntt_shared_memory_variant_gpu(mode):
     _rerun({"MB200_NTT_SMEM": mode}, "ntt or h_coefficients or prove")
