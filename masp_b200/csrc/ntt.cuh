@@ -37,9 +37,14 @@ struct NttArgs {
     const Fr* srcb;
     const Fr* srcc;
     Fr k1, k2;
+    // EXT kernels only (six-transform H pipeline): srcb without srcc = plain product on load;
+    // sub: after out_scale, val = (val - sub[o] * k3) * k2 on the last store
+    const Fr* sub;
+    size_t sub_stride;
+    Fr k3;
 };
 
-template <int K>
+template <int K, bool EXT = false>
 MB_HD void ntt_body(const NttArgs& a, size_t tid) {
     constexpr int R = 1 << K;
     const uint32_t n = 1u << a.log_n;
@@ -56,8 +61,12 @@ MB_HD void ntt_body(const NttArgs& a, size_t tid) {
             v[r] = src[idx];
             if (a.srcb) {
                 Fr b = a.srcb[item * a.src_stride + idx];
-                Fr c = a.srcc[item * a.src_stride + idx];
-                v[r] = Fr::sub(Fr::mul(Fr::mul(v[r], b), a.k1), Fr::mul(c, a.k2));
+                if (EXT && !a.srcc) {
+                    v[r] = Fr::mul(Fr::mul(v[r], b), Fr::r2());
+                } else {
+                    Fr c = a.srcc[item * a.src_stride + idx];
+                    v[r] = Fr::sub(Fr::mul(Fr::mul(v[r], b), a.k1), Fr::mul(c, a.k2));
+                }
             }
             if (a.in_scale) v[r] = Fr::mul(v[r], a.in_scale[idx]);
         } else {
@@ -105,9 +114,16 @@ MB_HD void ntt_body(const NttArgs& a, size_t tid) {
         uint32_t o = j0 + (uint32_t)q * a.ns;
         Fr val = v[i];
         if (a.out_scale) val = Fr::mul(val, a.out_scale[o]);
+        if (EXT && a.sub) val = Fr::mul(Fr::sub(val, Fr::mul(a.sub[item * a.sub_stride + o], a.k3)), a.k2);
         dst[o] = val;
     }
 }
+MB_HD void ntt1x_body(const NttArgs& a, size_t tid) { ntt_body<1, true>(a, tid); }
+MB_HD void ntt2x_body(const NttArgs& a, size_t tid) { ntt_body<2, true>(a, tid); }
+MB_HD void ntt3x_body(const NttArgs& a, size_t tid) { ntt_body<3, true>(a, tid); }
+MB_K_NTT(ntt_pass_r2_ext, NttArgs, ntt1x_body, 128)
+MB_K_NTT(ntt_pass_r4_ext, NttArgs, ntt2x_body, 128)
+MB_K_NTT(ntt_pass_r8_ext, NttArgs, ntt3x_body, 128)
 MB_HD void ntt1_body(const NttArgs& a, size_t tid) { ntt_body<1>(a, tid); }
 MB_HD void ntt2_body(const NttArgs& a, size_t tid) { ntt_body<2>(a, tid); }
 MB_HD void ntt3_body(const NttArgs& a, size_t tid) { ntt_body<3>(a, tid); }
@@ -215,10 +231,10 @@ struct NttPlan {
     const Fr* srcc = nullptr;
     uint32_t src_len = 0;  // 0 = n
     bool inverse = false;
-    // shared-memory path only (ntt_smem.cuh): after out_scale, val = (val - sub[o] * sub_k) * post_k
+    // six-transform H pipeline: after out_scale, val = (val - sub[o] * sub_k) * post_k on the last store
     const Fr* sub = nullptr;
     size_t sub_stride = 0;
-    Fr sub_k, post_k;
+    Fr sub_k{}, post_k{};
 };
 
 }  // namespace mb
@@ -308,7 +324,16 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
         a.srcc = first ? p.srcc : nullptr;
         a.k1 = d.k1;
         a.k2 = d.k2;
-        if (K == 3) launch_ntt_r8(a, s);
+        a.sub = last ? p.sub : nullptr;
+        a.sub_stride = p.sub_stride;
+        a.k3 = p.sub_k;
+        const bool ext = (a.srcb && !a.srcc) || a.sub;   // six-transform H pipeline only
+        if (a.sub) a.k2 = p.post_k;
+        if (ext) {
+            if (K == 3) launch_ntt_pass_r8_ext(a, s);
+            else if (K == 2) launch_ntt_pass_r4_ext(a, s);
+            else launch_ntt_pass_r2_ext(a, s);
+        } else if (K == 3) launch_ntt_r8(a, s);
         else if (K == 2) launch_ntt_pass_r4(a, s);
         else launch_ntt_pass_r2(a, s);
         cur = a.dst;
@@ -333,8 +358,12 @@ inline void h_pipeline(const NttDomain& d, uint32_t batch, uint32_t rows, const 
     p1.inverse = true;
     p1.src_len = rows;
     ntt_run(d, p1, batch * 3, abc, poly_stride, work2, n, work0, work1, s);
-    if ((ntt_smem_mode() & 4) && ntt_smem_supported(d.log_n)) {
-        // Opt-in: SIX transforms.  The inverse coset transform is linear, so
+    static const bool six_env = [] {
+        const char* e = getenv("MB200_H_SIX");
+        return e && *e && *e != '0';
+    }();
+    if (six_env || ((ntt_smem_mode() & 4) && ntt_smem_supported(d.log_n))) {
+        // Opt-in (MB200_H_SIX=1 with either NTT path, or MB200_NTT_SMEM=5|7): SIX transforms.  The inverse coset transform is linear, so
         //   icoset[(a b - c)(g w^i) / (g^m - 1)] = (icoset[(a b)(g w^i)] - c(X)) / (g^m - 1)
         // coefficient by coefficient, and c(X) is already there after step 1: the coset transform
         // of c is never needed.  Same field elements as the seven-transform form for ANY rows

@@ -161,9 +161,11 @@ def test_ntt_shared_memory_variant():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     runs = {}
-    procs = {mode: subprocess.Popen([sys.executable, "-c", _NTT_SMEM_CHILD, root],
-                                    env=dict(os.environ, MB200_NTT_SMEM=mode), stdout=subprocess.PIPE,
-                                    stderr=subprocess.PIPE, text=True) for mode in ("0", "1", "5")}
+    envs = {"0": {"MB200_NTT_SMEM": "0"}, "1": {"MB200_NTT_SMEM": "1"}, "5": {"MB200_NTT_SMEM": "5"},
+            "six": {"MB200_NTT_SMEM": "0", "MB200_H_SIX": "1"}}
+    procs = {mode: subprocess.Popen([sys.executable, "-c", _NTT_SMEM_CHILD, root], env=dict(os.environ, **extra),
+                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for mode, extra in envs.items()}
     for mode, pr in procs.items():
         out, err = pr.communicate(timeout=900)
         assert pr.returncode == 0, err[-2000:]
@@ -172,6 +174,7 @@ def test_ntt_shared_memory_variant():
     # mode 5: the H pipeline with six transforms (the coset transform of c is never needed because the
     # inverse coset transform is linear): same coefficients for satisfied AND unsatisfied rows
     assert [l for l in runs["5"] if l[0] == "h"] == [l for l in runs["0"] if l[0] == "h"]
+    assert [l[:5] for l in runs["six"]] == [l[:5] for l in runs["0"]]   # MB200_H_SIX=1 on the default kernels
     for base, smem in zip(runs["0"], runs["1"]):
         if base[0] == "h":
             assert base == smem

@@ -11,6 +11,7 @@ shipped path is judged by.  scripts/gpu_r2_variants.sh runs these and the A/B be
                             (2 global passes instead of 6); =2 stores kernel 1's contiguous runs with
                             TMA bulk copies (cp.async.bulk.global.shared::cta); =5 / =7 run the H pipeline with six
                             transforms instead of seven.
+  * MB200_H_SIX=1           csrc/ntt.cuh: the H pipeline with six transforms on the default pass-per-launch NTT.
 """
 import os
 import subprocess
@@ -44,3 +45,9 @@ def test_accumulate_lockstep_variant_gpu(level):
 @pytest.mark.parametrize("mode", ["1", "2", "5", "7"])
 def test_ntt_shared_memory_variant_gpu(mode):
     _rerun({"MB200_NTT_SMEM": mode}, "ntt or h_coefficients or prove")
+
+
+@enabled
+@pytest.mark.gpu
+def test_h_six_transforms_variant_gpu():
+    _rerun({"MB200_H_SIX": "1"}, "h_coefficients or prove")
