@@ -341,6 +341,47 @@ void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s, boo
 #else
 void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s, bool prefetch);
 #endif
+// G2 with the accumulator in SHARED memory (opt-in, MB200_ACC_G2_SMEM=1; not yet measured on a B200).
+// msm_accumulate_g2 is the one register-starved kernel of the path: 255 registers, 1.2 KB of spill code,
+// 8 warps per SM.  Its XYZZ<Fp2> accumulator alone is 96 words that live across the whole loop; parked
+// in shared memory (97-word stride per thread: conflict-free word accesses) it costs ~200 LDS / STS per
+// ~9 000-IMAD addition and frees the registers for the multiplier.
+#if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G2)
+static const int ACC_G2_SMEM_BLOCK = 128, ACC_G2_SMEM_STRIDE = 97;
+__global__ void __launch_bounds__(ACC_G2_SMEM_BLOCK, 3) msm_accumulate_g2_smem(const AccArgs<Fp2> a) {
+    extern __shared__ uint32_t acc_g2_sm[];
+    const size_t tid = (size_t)blockIdx.x * ACC_G2_SMEM_BLOCK + threadIdx.x;
+    if (tid >= *a.ntasks) return;
+    XYZZ<Fp2>& acc = *reinterpret_cast<XYZZ<Fp2>*>(acc_g2_sm + ACC_G2_SMEM_STRIDE * threadIdx.x);
+    const uint32_t t = a.order[tid];
+    const uint32_t n = a.task_len[t];
+    const uint32_t* e = a.entries + a.task_start[t];
+    acc = XYZZ<Fp2>::inf();
+    MB_NOUNROLL
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t ent = e[i];
+        Affine<Fp2> q = a.table[ent >> 1];
+        xyzz_madd(acc, q, (ent & 1) != 0);
+    }
+    a.partials[t] = acc;
+}
+void launch_msm_accumulate_g2_smem(const AccArgs<Fp2>& a, cudaStream_t s) {
+    if (!a.nthreads) return;
+    const int bytes = ACC_G2_SMEM_BLOCK * ACC_G2_SMEM_STRIDE * 4;
+    static const bool attr = [] {
+        MB_CUDA(cudaFuncSetAttribute(msm_accumulate_g2_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ACC_G2_SMEM_BLOCK * ACC_G2_SMEM_STRIDE * 4));
+        return true;
+    }();
+    (void)attr;
+    msm_accumulate_g2_smem<<<(unsigned)((a.nthreads + ACC_G2_SMEM_BLOCK - 1) / ACC_G2_SMEM_BLOCK), ACC_G2_SMEM_BLOCK,
+                             bytes, s>>>(a);
+    MB_CUDA(cudaGetLastError());
+    ::mb::g_launches++;
+}
+#else
+void launch_msm_accumulate_g2_smem(const AccArgs<Fp2>& a, cudaStream_t s);
+#endif
 #if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G2)
 __global__ void __launch_bounds__(256, 1) msm_accumulate_g2_lockstep(const AccArgs<Fp2> a) { acc_lockstep_body<Fp2, 256, false>(a); }
 void launch_msm_accumulate_g2_lockstep(const AccArgs<Fp2>& a, cudaStream_t s) {
@@ -513,6 +554,11 @@ template <>
 inline void launch_acc<Fp2>(const AccArgs<Fp2>& a, cudaStream_t s) {
 #ifndef MB200_EMU
     if (msm_acc_lockstep() == 2 && !a.direct) return launch_msm_accumulate_g2_lockstep(a, s);
+    static const bool g2_smem = [] {
+        const char* e = getenv("MB200_ACC_G2_SMEM");
+        return e && *e && *e != '0';
+    }();
+    if (g2_smem && !a.direct) return launch_msm_accumulate_g2_smem(a, s);
 #endif
     launch_msm_accumulate_g2(a, s);
 }
