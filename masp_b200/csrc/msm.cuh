@@ -341,6 +341,39 @@ void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s, boo
 #else
 void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s, bool prefetch);
 #endif
+// G1 with the accumulator in shared memory (opt-in, MB200_ACC_G1_SMEM=1; not yet measured on a B200): the
+// same idea as for G2 below, here to fit FOUR 128-thread blocks per SM (<= 128 registers) without the spills
+// the register-capped build of the plain kernel had (profiles/r01_acc_128reg_ab.jsonl).
+#if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G1)
+static const int ACC_G1_SMEM_BLOCK = 128, ACC_G1_SMEM_STRIDE = 49;
+__global__ void __launch_bounds__(ACC_G1_SMEM_BLOCK, 4) msm_accumulate_g1_smem(const AccArgs<Fp> a) {
+    __shared__ uint32_t acc_g1_sm[ACC_G1_SMEM_BLOCK * ACC_G1_SMEM_STRIDE];
+    const size_t tid = (size_t)blockIdx.x * ACC_G1_SMEM_BLOCK + threadIdx.x;
+    if (tid >= *a.ntasks) return;
+    XYZZ<Fp>& acc = *reinterpret_cast<XYZZ<Fp>*>(acc_g1_sm + ACC_G1_SMEM_STRIDE * threadIdx.x);
+    const uint32_t t = a.order[tid];
+    const uint32_t n = a.task_len[t];
+    const uint32_t* e = a.entries + a.task_start[t];
+    acc = XYZZ<Fp>::inf();
+    MB_NOUNROLL
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t ent = e[i];
+        Affine<Fp> q = a.table[ent >> 1];
+        xyzz_madd(acc, q, (ent & 1) != 0);
+    }
+    a.partials[t] = acc;
+}
+void launch_msm_accumulate_g1_smem(const AccArgs<Fp>& a, cudaStream_t s) {
+    if (!a.nthreads) return;
+    msm_accumulate_g1_smem<<<(unsigned)((a.nthreads + ACC_G1_SMEM_BLOCK - 1) / ACC_G1_SMEM_BLOCK), ACC_G1_SMEM_BLOCK, 0,
+                             s>>>(a);
+    MB_CUDA(cudaGetLastError());
+    ::mb::g_launches++;
+}
+#else
+void launch_msm_accumulate_g1_smem(const AccArgs<Fp>& a, cudaStream_t s);
+#endif
+
 // G2 with the accumulator in SHARED memory (opt-in, MB200_ACC_G2_SMEM=1; not yet measured on a B200).
 // msm_accumulate_g2 is the one register-starved kernel of the path: 255 registers, 1.2 KB of spill code,
 // 8 warps per SM.  Its XYZZ<Fp2> accumulator alone is 96 words that live across the whole loop; parked
@@ -547,6 +580,11 @@ template <>
 inline void launch_acc<Fp>(const AccArgs<Fp>& a, cudaStream_t s) {
 #ifndef MB200_EMU
     if (msm_acc_lockstep() >= 1 && !a.direct) return launch_msm_accumulate_g1_lockstep(a, s, msm_acc_lockstep() == 3);
+    static const bool g1_smem = [] {
+        const char* e = getenv("MB200_ACC_G1_SMEM");
+        return e && *e && *e != '0';
+    }();
+    if (g1_smem && !a.direct) return launch_msm_accumulate_g1_smem(a, s);
 #endif
     launch_msm_accumulate_g1(a, s);
 }

@@ -11,6 +11,8 @@ shipped path is judged by.  scripts/gpu_r2_variants.sh runs these and the A/B be
                             (2 global passes instead of 6); =2 stores kernel 1's contiguous runs with
                             TMA bulk copies (cp.async.bulk.global.shared::cta); =5 / =7 run the H pipeline with six
                             transforms instead of seven.
+  * MB200_ACC_G1_SMEM=1     csrc/msm.cuh: msm_accumulate_g1 with its accumulator in shared memory: 128 registers
+                            with 4 bytes of spill, four blocks (16 warps) per SM instead of three.
   * MB200_ACC_G2_SMEM=1     csrc/msm.cuh: msm_accumulate_g2 with its XYZZ<Fp2> accumulator in shared memory
                             (168 registers and 12 warps per SM instead of 255 and 8).
   * MB200_H_SIX=1           csrc/ntt.cuh: the H pipeline with six transforms on the default pass-per-launch NTT.
@@ -59,3 +61,9 @@ def test_h_six_transforms_variant_gpu():
 @pytest.mark.gpu
 def test_g2_shared_accumulator_variant_gpu():
     _rerun({"MB200_ACC_G2_SMEM": "1"}, "msm_g2 or prove")
+
+
+@enabled
+@pytest.mark.gpu
+def test_g1_shared_accumulator_variant_gpu():
+    _rerun({"MB200_ACC_G1_SMEM": "1"}, "msm or prove or proof")
