@@ -285,7 +285,7 @@ MB_K_MSM_G1(msm_accumulate_g1, AccArgs<Fp>, acc_g1_body, 128)
 MB_K_MSM_G2(msm_accumulate_g2, AccArgs<Fp2>, acc_g2_body, 64)
 
 // Lock-step variant (opt-in, MB200_ACC_LOCKSTEP=1: G1, =2: G1 and G2, =3: G1 with an L2 prefetch of the
-// next table point; not yet measured on a B200).
+// next table point, =4: G1 with 512 threads and the accumulators in shared memory; not yet measured on a B200).
 // Why: in the profile of msm_accumulate_g1 the second-largest stall after the IMAD dependency `wait`
 // is `no_instructions` (16 % of the samples): the loop body is ~72 KB of straight-line code and the
 // 12 resident warps of an SM sit at 12 different places in it, so every warp streams the whole body
@@ -372,6 +372,47 @@ void launch_msm_accumulate_g1_smem(const AccArgs<Fp>& a, cudaStream_t s) {
 }
 #else
 void launch_msm_accumulate_g1_smem(const AccArgs<Fp>& a, cudaStream_t s);
+#endif
+
+// Both at once (opt-in, MB200_ACC_LOCKSTEP=4): one 512-thread block per SM (16 warps at <= 128 registers),
+// accumulators in shared memory, a barrier per iteration.
+#if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G1)
+static const int ACC_G1_LS4_BLOCK = 512;
+__global__ void __launch_bounds__(ACC_G1_LS4_BLOCK, 1) msm_accumulate_g1_lockstep_smem(const AccArgs<Fp> a) {
+    extern __shared__ uint32_t acc_g1_ls_sm[];
+    const size_t tid = (size_t)blockIdx.x * ACC_G1_LS4_BLOCK + threadIdx.x;
+    const bool live = tid < *a.ntasks;
+    const uint32_t t = live ? a.order[tid] : 0;
+    const uint32_t n = live ? a.task_len[t] : 0;
+    const uint32_t* e = a.entries + (live ? a.task_start[t] : 0);
+    XYZZ<Fp>& acc = *reinterpret_cast<XYZZ<Fp>*>(acc_g1_ls_sm + ACC_G1_SMEM_STRIDE * threadIdx.x);
+    acc = XYZZ<Fp>::inf();
+    MB_NOUNROLL
+    for (uint32_t i = 0; __syncthreads_or(i < n); ++i) {
+        if (i < n) {
+            uint32_t ent = e[i];
+            Affine<Fp> q = a.table[ent >> 1];
+            xyzz_madd(acc, q, (ent & 1) != 0);
+        }
+    }
+    if (live) a.partials[t] = acc;
+}
+void launch_msm_accumulate_g1_lockstep_smem(const AccArgs<Fp>& a, cudaStream_t s) {
+    if (!a.nthreads) return;
+    const int bytes = ACC_G1_LS4_BLOCK * ACC_G1_SMEM_STRIDE * 4;
+    static const bool attr = [] {
+        MB_CUDA(cudaFuncSetAttribute(msm_accumulate_g1_lockstep_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     ACC_G1_LS4_BLOCK * ACC_G1_SMEM_STRIDE * 4));
+        return true;
+    }();
+    (void)attr;
+    msm_accumulate_g1_lockstep_smem<<<(unsigned)((a.nthreads + ACC_G1_LS4_BLOCK - 1) / ACC_G1_LS4_BLOCK),
+                                      ACC_G1_LS4_BLOCK, bytes, s>>>(a);
+    MB_CUDA(cudaGetLastError());
+    ::mb::g_launches++;
+}
+#else
+void launch_msm_accumulate_g1_lockstep_smem(const AccArgs<Fp>& a, cudaStream_t s);
 #endif
 
 // G2 with the accumulator in SHARED memory (opt-in, MB200_ACC_G2_SMEM=1; not yet measured on a B200).
@@ -579,6 +620,7 @@ inline uint32_t msm_acc_lockstep() {
 template <>
 inline void launch_acc<Fp>(const AccArgs<Fp>& a, cudaStream_t s) {
 #ifndef MB200_EMU
+    if (msm_acc_lockstep() == 4 && !a.direct) return launch_msm_accumulate_g1_lockstep_smem(a, s);
     if (msm_acc_lockstep() >= 1 && !a.direct) return launch_msm_accumulate_g1_lockstep(a, s, msm_acc_lockstep() == 3);
     static const bool g1_smem = [] {
         const char* e = getenv("MB200_ACC_G1_SMEM");

@@ -6,7 +6,8 @@ a variant that has never executed on the hardware must not be able to stop the s
 shipped path is judged by.  scripts/gpu_r2_variants.sh runs these and the A/B bench.
 
   * MB200_ACC_LOCKSTEP=1|2  csrc/msm.cuh: one block per SM, a barrier per bucket-addition iteration
-                            (instruction-cache locality), G1 or G1 + G2; 3 = G1 with an L2 prefetch of the next table point.
+                            (instruction-cache locality), G1 or G1 + G2; 3 = G1 with an L2 prefetch of the next table point;
+                            4 = G1 with 512 threads per SM and the accumulators in shared memory.
   * MB200_NTT_SMEM=1|2      csrc/ntt_smem.cuh: the Stockham transform as two shared-memory kernels
                             (2 global passes instead of 6); =2 stores kernel 1's contiguous runs with
                             TMA bulk copies (cp.async.bulk.global.shared::cta); =5 / =7 run the H pipeline with six
@@ -39,7 +40,7 @@ def _rerun(env_extra, select, timeout=900):
 
 @enabled
 @pytest.mark.gpu
-@pytest.mark.parametrize("level", ["1", "2", "3"])
+@pytest.mark.parametrize("level", ["1", "2", "3", "4"])
 def test_accumulate_lockstep_variant_gpu(level):
     _rerun({"MB200_ACC_LOCKSTEP": level}, "msm or prove or proof")
 
