@@ -11,6 +11,9 @@ Mirrors, with the reference's names, argument order and error behaviour:
     ProofGenerationKey / ViewingKey / Diversifier / PaymentAddress / Note / ValueCommitment
     (sapling.rs:196-225, 333-360, 453-480, 503-565, 796-863), AllowedConversion
     (convert.rs:23-120), RedJubjub sign / verify (sapling/redjubjub.rs:133-260)
+  * SaplingVerificationContext / BatchValidator      masp_proofs/src/sapling/verifier.rs:19-215,
+    (the verifier-side callers of verify_proof)      verifier/single.rs, verifier/batch.rs:60-243
+  * write_v5_sapling / read_v5_sapling               masp_primitives/src/transaction.rs:612-720, 746-806
   * BatchingTxProver: SURVEY.md §8(f)-2 -- `*_proof` calls update the context and enqueue,
     every proof of the transaction is produced by one launch per circuit when the first
     result is needed (binding_sig at the latest).
