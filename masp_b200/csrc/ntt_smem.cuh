@@ -103,9 +103,17 @@ MB_HD void ntt_fused_item(Fr* v, const NttFusedArgs& a, uint32_t kk_glob, uint32
     }
 }
 
+// Element i of an array lives at slot i ^ ((i >> 3) & 7): a permutation inside every aligned group of eight.
+// The first radix-8 pass writes 8 j + q for consecutive j (256 bytes apart: one bank group for the whole
+// quarter-warp); swizzled, those eight lanes land on eight different slots.  Reads of consecutive elements
+// and the strided writes of the later passes stay conflict-free under it.  `nat` = natural order (the layout
+// the TMA bulk store needs for the last pass of kernel 1).
+MB_HD uint32_t ntt_slot(uint32_t i, bool nat) { return nat ? i : (i ^ ((i >> 3) & 7u)); }
+
 // one local pass over the block's C arrays of 2^L elements; every thread owns 8 values
 template <int K>
-MB_BLOCK_FN void ntt_fused_pass(const NttFusedArgs& a, Fr* sm, Fr (*regs)[8], uint32_t g0, uint32_t ns_loc) {
+MB_BLOCK_FN void ntt_fused_pass(const NttFusedArgs& a, Fr* sm, Fr (*regs)[8], uint32_t g0, uint32_t ns_loc,
+                                bool write_nat) {
     constexpr int R = 1 << K;
     constexpr int ITEMS = 8 / R;               // work items per thread
     const uint32_t Ln = 1u << a.L, Lp = Ln + 1, per = Ln >> K, S = 1u << (a.log_n - a.L);
@@ -116,7 +124,7 @@ MB_BLOCK_FN void ntt_fused_pass(const NttFusedArgs& a, Fr* sm, Fr (*regs)[8], ui
             uint32_t w = t + (uint32_t)it * NTT_SMEM_THREADS;
             uint32_t c = w / per, j = w - c * per;
             MB_UNROLL
-            for (int r = 0; r < R; ++r) v[it * R + r] = sm[c * Lp + j + (uint32_t)r * per];
+            for (int r = 0; r < R; ++r) v[it * R + r] = sm[c * Lp + ntt_slot(j + (uint32_t)r * per, false)];
         }
     }
     MB_BLOCK_SYNC();
@@ -136,7 +144,7 @@ MB_BLOCK_FN void ntt_fused_pass(const NttFusedArgs& a, Fr* sm, Fr (*regs)[8], ui
                 int q = 0;
                 MB_UNROLL
                 for (int b = 0; b < K; ++b) q |= ((i >> b) & 1) << (K - 1 - b);
-                sm[c * Lp + j0 + (uint32_t)q * ns_loc] = v[it * R + i];
+                sm[c * Lp + ntt_slot(j0 + (uint32_t)q * ns_loc, write_nat)] = v[it * R + i];
             }
         }
     }
@@ -171,18 +179,20 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
                 }
                 if (a.in_scale) x = Fr::mul(x, a.in_scale[idx]);
             }
-            sm[c * Lp + s] = x;
+            sm[c * Lp + ntt_slot(s, false)] = x;
         }
     }
     MB_BLOCK_SYNC();
+    // the last pass of kernel 1 leaves natural order when the TMA bulk store follows
+    const bool nat_out = a.group == 0 && a.bulk_store;
     uint32_t left = a.L, ns = 1;
     while (left >= 3) {
-        ntt_fused_pass<3>(a, sm, regs, g0, ns);
+        ntt_fused_pass<3>(a, sm, regs, g0, ns, nat_out && left == 3);
         ns <<= 3;
         left -= 3;
     }
-    if (left == 2) ntt_fused_pass<2>(a, sm, regs, g0, ns);
-    if (left == 1) ntt_fused_pass<1>(a, sm, regs, g0, ns);
+    if (left == 2) ntt_fused_pass<2>(a, sm, regs, g0, ns, nat_out);
+    if (left == 1) ntt_fused_pass<1>(a, sm, regs, g0, ns, nat_out);
     if (a.group == 0) {
         // array c is the contiguous run dst[(g0 + c) * 2^L ...]
 #ifndef MB200_EMU
@@ -211,7 +221,7 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
             for (int i = 0; i < 8; ++i) {
                 uint32_t e = t + (uint32_t)i * NTT_SMEM_THREADS;
                 uint32_t c = e >> a.L, k = e & (Ln - 1);
-                dst[(size_t)(g0 + c) * Ln + k] = sm[c * Lp + k];
+                dst[(size_t)(g0 + c) * Ln + k] = sm[c * Lp + ntt_slot(k, nat_out)];
             }
         }
     } else {
@@ -221,7 +231,7 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
                 uint32_t e = t + (uint32_t)i * NTT_SMEM_THREADS;
                 uint32_t c = e & (C - 1), o = e >> a.logC;
                 uint32_t idx = g0 + c + o * S;
-                Fr val = sm[c * Lp + o];
+                Fr val = sm[c * Lp + ntt_slot(o, false)];
                 if (a.out_scale) val = Fr::mul(val, a.out_scale[idx]);
                 if (a.sub) val = Fr::mul(Fr::sub(val, Fr::mul(a.sub[item * a.sub_stride + idx], a.k3)), a.k2);
                 dst[idx] = val;

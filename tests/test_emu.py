@@ -162,6 +162,7 @@ def test_ntt_shared_memory_variant():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     runs = {}
     envs = {"0": {"MB200_NTT_SMEM": "0"}, "1": {"MB200_NTT_SMEM": "1"}, "5": {"MB200_NTT_SMEM": "5"},
+            "3": {"MB200_NTT_SMEM": "3"},   # natural-order output of kernel 1 (the layout its TMA bulk store reads)
             "six": {"MB200_NTT_SMEM": "0", "MB200_H_SIX": "1"}}
     procs = {mode: subprocess.Popen([sys.executable, "-c", _NTT_SMEM_CHILD, root], env=dict(os.environ, **extra),
                                     stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
@@ -170,7 +171,8 @@ def test_ntt_shared_memory_variant():
         out, err = pr.communicate(timeout=900)
         assert pr.returncode == 0, err[-2000:]
         runs[mode] = [l.split() for l in out.strip().splitlines()]
-    assert len(runs["0"]) == len(runs["1"]) == len(runs["5"]) == 4 * 4 + 4
+    assert len(runs["0"]) == len(runs["1"]) == len(runs["5"]) == len(runs["3"]) == 4 * 4 + 4
+    assert [l[:5] for l in runs["3"]] == [l[:5] for l in runs["0"]]
     # mode 5: the H pipeline with six transforms (the coset transform of c is never needed because the
     # inverse coset transform is linear): same coefficients for satisfied AND unsatisfied rows
     assert [l for l in runs["5"] if l[0] == "h"] == [l for l in runs["0"] if l[0] == "h"]
