@@ -71,8 +71,28 @@ r0 = blk.index("let roots = [")
 roots = re.findall(r'"([0-9a-f]{64})"', blk[r0:blk.index("];", r0)])
 assert len(commitments) == 16 and len(roots) == 16
 
+# ZIP 32 vectors (zip32/sapling.rs:1372-2135): ask, nsk -> ak, nk -> ivk (and the internal branch), plus the
+# diversifiers the reference found valid (d0, d1, d2, dmax).  They pin ak = ask * G_spend, nk = nsk * G_proof and
+# CRH^ivk (ViewingKey::ivk, sapling.rs:338-355) on values the reference asserts at zip32/sapling.rs:2074-2106.
+src = open(os.path.join(prim, "zip32/sapling.rs")).read()
+src = src[src.index("let test_vectors = vec!["):]
+src = src[:src.index("assert_eq!(test_vectors.len()")]
+keys = []
+for m in re.finditer(r"TestVector \{(.*?)\n            \},", src, re.S):
+    body = m.group(1)
+
+    def opt(name):
+        mm = re.search(r"\b%s: (None|(?:Some\()?\[(.*?)\])" % name, body, re.S)
+        if mm is None or mm.group(1) == "None":
+            return None
+        return bytes(int(x, 16) for x in re.findall(r"0x([0-9a-f]{2})", mm.group(2))).hex()
+
+    keys.append({k: opt(k) for k in ("ask", "nsk", "ak", "nk", "ivk", "d0", "d1", "d2", "dmax", "internal_nsk",
+                                     "internal_nk", "internal_ivk")})
+assert len(keys) == 5 and all(len(k["ak"]) == 64 and len(k["ivk"]) == 64 for k in keys)
+
 out = {"asset_identifier": b"testtesttesttesttesttesttesttest".hex(), "generators": gens, "note_commitments": notes,
-       "empty_roots": empty_roots, "tree_commitments": commitments, "tree_roots": roots}
+       "zip32_keys": keys, "empty_roots": empty_roots, "tree_commitments": commitments, "tree_roots": roots}
 dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sapling_vectors.json")
 json.dump(out, open(dst, "w"), indent=0)
-print(len(notes), "note vectors, 11 generators, 33 empty roots, 16 tree roots ->", dst)
+print(len(notes), "note vectors, 11 generators, 33 empty roots, 16 tree roots, %d key vectors ->" % len(keys), dst)

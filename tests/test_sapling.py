@@ -7,7 +7,8 @@ tests/golden/make_sapling_vectors.py):
     exactly as the reference's tests do (constants.rs:323-375);
   * HEX_EMPTY_ROOTS, the 33 empty roots of the commitment tree (merkle_tree.rs:912-946), and the 16
     commitments / roots of test_sapling_tree (merkle_tree.rs:1091-1135);
-  * the note commitments of the note-encryption vectors (sapling/note_encryption.rs:1357-1361).
+  * the note commitments of the note-encryption vectors (sapling/note_encryption.rs:1357-1361);
+  * the ZIP 32 key vectors (zip32/sapling.rs:1372-2135): ask, nsk -> ak, nk -> ivk, found diversifiers.
 
 and cross-checked against the product's own circuits: the public inputs this module computes
 natively (as sapling/prover.rs:121-145 does) equal the input assignment the Spend / Output / Convert
@@ -108,6 +109,31 @@ def test_note_commitments_match_the_reference_vectors():
         note = to.create_note(asset, tv["v"], S.Rseed.before_zip212(rcm))
         assert note is not None
         assert note.cmu().to_bytes(32, "little").hex() == tv["cmu"]
+
+
+def test_zip32_key_vectors_match_the_reference():
+    """zip32/sapling.rs:2074-2106: ak = ask * G_spend, nk = nsk * G_proof, ivk = CRH^ivk(ak, nk), for the external
+    and the internal branch, and every diversifier the reference lists as found is valid under group_hash."""
+    le = lambda h: int.from_bytes(bytes.fromhex(h), "little")
+    for tv in GOLD["zip32_keys"]:
+        ak, nk = S.jj_from_bytes(bytes.fromhex(tv["ak"])), S.jj_from_bytes(bytes.fromhex(tv["nk"]))
+        assert ak is not None and nk is not None
+        if tv["ask"]:
+            assert S.jj_to_bytes(S.jj_mul(S.SPENDING_KEY_GENERATOR, le(tv["ask"]))).hex() == tv["ak"]
+        if tv["nsk"]:
+            vk = S.ProofGenerationKey(ak, le(tv["nsk"])).to_viewing_key()
+            assert S.jj_to_bytes(vk.nk).hex() == tv["nk"]
+        assert S.ViewingKey(ak, nk).ivk() == le(tv["ivk"])
+        nk_int = S.jj_from_bytes(bytes.fromhex(tv["internal_nk"]))
+        if tv["internal_nsk"]:
+            assert S.jj_mul(S.PROOF_GENERATION_KEY_GENERATOR, le(tv["internal_nsk"])) == nk_int
+        assert S.ViewingKey(ak, nk_int).ivk() == le(tv["internal_ivk"])
+        for d in ("d0", "d1", "d2", "dmax"):
+            if tv[d]:
+                g_d = S.Diversifier(bytes.fromhex(tv[d])).g_d()
+                assert g_d is not None and S.jj_mul(g_d, S.JUBJUB_ORDER) == S.IDENTITY
+                addr = S.ViewingKey(ak, nk).to_payment_address(S.Diversifier(bytes.fromhex(tv[d])))
+                assert addr is not None and addr.pk_d == S.jj_mul(g_d, le(tv["ivk"]))
 
 
 def test_asset_type_rules():
