@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 opener for the opt-in kernel variants written (unmeasured) at the end of round 1.
-#   gpurun --timeout 900 -- 'bash scripts/gpu_r2_variants.sh parity'   # byte-exactness of every variant (~6 min)
+#   gpurun --timeout 1200 -- 'bash scripts/gpu_r2_variants.sh parity'  # byte-exactness of every variant (each child run is cut at 300 s)
 #   gpurun --timeout 900 -- 'bash scripts/gpu_r2_variants.sh ab'       # headline bench, one JSON line per setting (~8 min)
 #   gpurun --timeout 600 -- 'bash scripts/gpu_r2_variants.sh ncu'      # launch times / stalls of the new kernels
 # Settings: "<MB200_ACC_LOCKSTEP> <x>", x = MB200_NTT_SMEM value, or six (MB200_H_SIX), g1 / g2 / g12 (MB200_ACC_G*_SMEM).

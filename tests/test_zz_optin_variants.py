@@ -29,7 +29,7 @@ enabled = pytest.mark.skipif(os.environ.get("MB200_TEST_VARIANTS") != "1",
                              reason="opt-in variants: set MB200_TEST_VARIANTS=1")
 
 
-def _rerun(env_extra, select, timeout=900):
+def _rerun(env_extra, select, timeout=300):
     env = dict(os.environ, **env_extra)
     env.pop("MB200_TEST_VARIANTS", None)
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-x", "-q", "-m",
