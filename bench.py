@@ -457,6 +457,8 @@ def main():
             "window_bits": {"h_l": params.window_hl, "a": params.window_a},
             "table_bytes_hbm": params.table_bytes, "algorithmic_bytes_per_proof": shape.algorithmic_bytes(),
             "setup_s": round(t_setup, 2), "key_synth_and_load_s": round(t_key, 2),
+            # opt-in kernel variants in effect (DESIGN.md "Runtime knobs"); empty = the shipped defaults
+            "knobs": {k: v for k, v in sorted(os.environ.items()) if k.startswith("MB200_") and v not in ("", "0")},
         },
         "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 192,
                 "ms_per_step": 1e3 * wall_e2e / args.steps},
