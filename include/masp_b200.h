@@ -17,8 +17,12 @@
  *   - scalars are 32-byte little-endian canonical integers < r
  *     (= PrimeField::to_repr of bls12_381::Scalar);
  *   - points use bellman's wire encodings (zkcrypto uncompressed / compressed).
- *   - one process drives one GPU (one rank per GPU under torch.distributed);
- *     calls are serialised internally.
+ *   - one process drives every GPU it passes to mb200_init -- the reference's prover is one
+ *     `&self` object shared by all threads (masp_proofs/src/prover.rs:27-33, 156-261): keys are
+ *     replicated to each device, a batch is cut into per-device slices (one host thread
+ *     enqueues each), standalone calls run on device_ids[0].  One rank per GPU under
+ *     torch.distributed (each rank passing its own device) works the same way.  Calls are
+ *     serialised internally.
  */
 #ifndef MASP_B200_H
 #define MASP_B200_H
@@ -44,11 +48,14 @@ extern "C" {
 
 typedef struct mb200_params mb200_params;
 
-/* Binds the library to one device (device_ids[0]; NULL / 0 = current device)
- * and creates its streams.  Fails with MB200_ECUDA when there is no usable
- * GPU: there is no CPU fallback. */
+/* Opens the listed devices (NULL / 0 = the current device; NULL / -1 = every visible device)
+ * and creates their streams and chunk contexts.  device_ids[0] is the primary device (standalone
+ * MSM / NTT / verification calls, the destination of split-MSM partials).  Fails with MB200_ECUDA
+ * when there is no usable GPU: there is no CPU fallback. */
 int mb200_init(const int* device_ids, int n_devices);
 int mb200_shutdown(void);
+/* devices opened by mb200_init (0 before it) */
+int mb200_device_count(void);
 
 /* groth16::Parameters::<Bls12>::read(reader, false) as called at
  * masp_proofs/src/lib.rs:336-341, plus the three density bitmaps bellman's
@@ -206,6 +213,19 @@ int mb200_g1_bases_upload(const uint8_t* bases_uncompressed, size_t n, void** de
 int mb200_dev_free(void* dev_ptr);
 int mb200_msm_g1_partial(const void* dev_bases, const uint8_t* scalars, size_t n, uint8_t out_partial[192]);
 int mb200_g1_sum_partials(const uint8_t* partials, size_t count, uint8_t out_uncompressed[96]);
+/* The same two steps without a host hop, for one-rank-per-GPU callers (BASELINE config 3 under
+ * torch.distributed): the partial is written to device memory (dev_partial: 192 bytes, e.g. a
+ * row of the tensor handed to ncclAllGather), and the gathered partials are added and encoded
+ * on the device (SURVEY.md kernel K6, partial_point_allgather_add). */
+int mb200_msm_g1_partial_device(const void* dev_bases, const uint8_t* scalars, size_t n, void* dev_partial);
+int mb200_g1_sum_partials_device(const void* dev_partials, size_t count, uint8_t out_uncompressed[96]);
+/* The single-process form: bases range-split over every opened device at upload; one call
+ * reduces each range on its GPU, moves the 192-byte partials GPU -> GPU (NVLink peer copies) to
+ * the primary device and adds them there. */
+typedef struct mb200_g1_bases mb200_g1_bases;
+int mb200_g1_bases_new(const uint8_t* bases_uncompressed, size_t n, mb200_g1_bases** out);
+void mb200_g1_bases_free(mb200_g1_bases* b);
+int mb200_msm_g1_bases(const mb200_g1_bases* b, const uint8_t* scalars, size_t n, uint8_t out_uncompressed[96]);
 
 /* EvaluationDomain::{fft, ifft, coset_fft, icoset_fft} in place on host data
  * (2^log_n scalars). */
@@ -218,13 +238,15 @@ int mb200_h_coeffs(const uint8_t* a_evals, const uint8_t* b_evals, const uint8_t
 int mb200_fr_mul(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 int mb200_fr_mul_device(const void* a, const void* b, size_t n, void* out);
 
-/* knobs: "chunk" proofs per in-flight chunk; "streams" in-flight chunks; "verify" 0/1 self-check */
+/* knobs: "chunk" proofs per in-flight chunk; "streams" in-flight chunks per device; "verify" 0/1/2 self-check;
+ * "profile" 0/1 event timing of the accumulation kernels (synchronises: measurement only) */
 int mb200_set_option(const char* name, long value);
 /* counters: "launches" (kernels launched so far), "acc_launches",
  * "acc_us" (device time of the bucket-accumulation kernels, microseconds;
  * "acc_bytes" their algorithmic bytes, 128 N per G1 and 224 N per G2 instance;
- * "last_batch_us" device time of the last prove call;
- * only measured while option "profile" = 1) */
+ * "last_batch_us" device time of the last prove call (max over devices);
+ * "devices"; "verified", "verify_failed";
+ * acc_* only measured while option "profile" = 1) */
 int mb200_get_counter(const char* name, double* value);
 /* device self-test of the register-level field / curve arithmetic against
  * straightforward 64-bit code; returns the number of mismatches (0 = pass) */

@@ -11,10 +11,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmasp_b200.so")
 
 SYMBOLS = [
-    "mb200_init", "mb200_shutdown", "mb200_params_load", "mb200_params_info", "mb200_params_free",
+    "mb200_init", "mb200_shutdown", "mb200_device_count", "mb200_params_load", "mb200_params_info", "mb200_params_free",
     "mb200_params_synth_size", "mb200_params_synthesize", "mb200_synth_points", "mb200_prove_batch",
     "mb200_prove_batch_device", "mb200_prove_submit", "mb200_prove_wait", "mb200_msm_g1", "mb200_msm_g2", "mb200_g1_bases_upload", "mb200_dev_free",
-    "mb200_msm_g1_partial", "mb200_g1_sum_partials", "mb200_ntt", "mb200_h_coeffs", "mb200_fr_mul",
+    "mb200_msm_g1_partial", "mb200_g1_sum_partials", "mb200_msm_g1_partial_device", "mb200_g1_sum_partials_device",
+    "mb200_g1_bases_new", "mb200_g1_bases_free", "mb200_msm_g1_bases", "mb200_ntt", "mb200_h_coeffs", "mb200_fr_mul",
     "mb200_fr_mul_device", "mb200_set_option", "mb200_get_counter", "mb200_selftest", "mb200_bench_fpmul", "mb200_bench_latency",
     "mb200_strerror", "mb200_last_error",
     "mb200_circuit_new", "mb200_circuit_free", "mb200_circuit_info", "mb200_circuit_hash", "mb200_circuit_densities",
@@ -39,6 +40,7 @@ def bind(path):
     u8p, vp, sz, u32, u64 = c.c_char_p, c.c_void_p, c.c_size_t, c.c_uint32, c.c_uint64
     L.mb200_init.argtypes = [c.POINTER(c.c_int), c.c_int]
     L.mb200_shutdown.argtypes = []
+    L.mb200_device_count.argtypes = []
     L.mb200_params_load.argtypes = [u8p, sz, u8p, u8p, u8p, c.POINTER(vp)]
     L.mb200_params_info.argtypes = [vp, c.POINTER(u64)]
     L.mb200_params_free.argtypes = [vp]
@@ -57,6 +59,12 @@ def bind(path):
     L.mb200_dev_free.argtypes = [vp]
     L.mb200_msm_g1_partial.argtypes = [vp, vp, sz, vp]
     L.mb200_g1_sum_partials.argtypes = [vp, sz, vp]
+    L.mb200_msm_g1_partial_device.argtypes = [vp, vp, sz, vp]
+    L.mb200_g1_sum_partials_device.argtypes = [vp, sz, vp]
+    L.mb200_g1_bases_new.argtypes = [vp, sz, c.POINTER(vp)]
+    L.mb200_g1_bases_free.argtypes = [vp]
+    L.mb200_g1_bases_free.restype = None
+    L.mb200_msm_g1_bases.argtypes = [vp, vp, sz, vp]
     L.mb200_ntt.argtypes = [vp, c.c_uint, c.c_int, c.c_int]
     L.mb200_h_coeffs.argtypes = [vp, vp, vp, sz, vp]
     L.mb200_fr_mul.argtypes = [vp, vp, sz, vp]

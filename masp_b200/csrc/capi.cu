@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <array>
 #include <map>
+#include <memory>
 #include <mutex>
+#include <thread>
 
 #include "host/circuit_obj.hpp"
 #include "prover.cuh"
@@ -13,82 +15,150 @@
 
 namespace mb {
 
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 MsmProfile g_msm_profile;
 
 // ---------------------------------------------------------------------------
-// process state
+// process state: one Device per GPU opened by mb200_init.  The reference's prover is ONE object
+// shared by every thread of the process (masp_proofs/src/prover.rs:27-33, 156-261: `&self`,
+// immutable parameters); here that object spans all opened GPUs: keys are replicated to every
+// device, a batch is cut into per-device slices, standalone calls run on device slot 0.
 // ---------------------------------------------------------------------------
 struct NttCache {
     NttDomain dom;
     DevBuf gpow;  // g^i, Montgomery (standalone coset_fft)
 };
-struct State {
-    bool inited = false;
-    int device = 0;
+struct TicketRes;
+struct Device {
+    int id = 0;      // CUDA ordinal
+    int slot = 0;    // index into State::devs
     cudaStream_t main = 0;
     std::vector<ProveCtx> ctxs;
+    cudaStream_t vstream[4] = {0, 0, 0, 0};  // the self-check's streams (round robin over chunks)
+    size_t next_v = 0;
+    size_t next_ctx = 0;  // chunks go round the contexts across batches, so consecutive batches overlap
+    std::map<unsigned, NttCache*> ntt;
+    MsmScratch msm;
+    std::vector<TicketRes*> res_free;
+    DevBuf peer_parts;  // slot 0 only: where the other devices' MSM partials land (K6)
+};
+struct State {
+    bool inited = false;
+    std::vector<std::unique_ptr<Device>> devs;
     uint32_t chunk = 64;
+    uint32_t n_streams = 3;
     int verify = 0;  // option "verify": 1 = check every proof before returning it (failure = MB200_EVERIFY),
                      // 2 = check and only count the failures (counter "verify_failed"; for measuring the cost)
     unsigned long long verify_failed = 0, verified = 0;
-    cudaStream_t vstream[4] = {0, 0, 0, 0};  // the self-check's streams (round robin over chunks)
-    size_t next_v = 0;
-    std::map<unsigned, NttCache*> ntt;
-    MsmScratch msm;
+    size_t next_dev = 0;  // small batches rotate over the devices
     std::mutex mu;
-    double last_batch_ms = 0;  // device time of the last prove call (CUDA events on the chunk streams)
+    double last_batch_ms = 0;  // device time of the last prove call (CUDA events on the chunk streams, max over devices)
 };
 static State g;
 
 static void require_init() {
     if (!g.inited) fail(MB200_ESTATE, "mb200_init has not been called%s", "");
 }
-static void set_ctx_count(size_t n) {
+// Make `d` the calling thread's current device (CUDA's current device is per host thread).
+static inline void use(const Device& d) {
 #ifndef MB200_EMU
-    for (auto& c : g.ctxs)
+    MB_CUDA(cudaSetDevice(d.id));
+#else
+    (void)d;
+#endif
+}
+static inline Device& dev0() {
+    require_init();
+    Device& d = *g.devs[0];
+    use(d);
+    return d;
+}
+
+// Runs fn(device) for every listed device, one host thread per device beyond the first, and
+// rethrows the first failure on the calling thread (fail() records its message per thread).
+template <class Fn>
+static void for_devices(const std::vector<Device*>& ds, Fn fn) {
+    if (ds.empty()) return;
+    if (ds.size() == 1) {
+        use(*ds[0]);
+        fn(*ds[0]);
+        return;
+    }
+    struct Outcome {
+        int code = 0;
+        char msg[256] = {0};
+    };
+    std::vector<Outcome> res(ds.size());
+    auto body = [&](size_t i) {
+        try {
+            use(*ds[i]);
+            fn(*ds[i]);
+        } catch (const Exc& e) {
+            res[i].code = e.code;
+            memcpy(res[i].msg, last_error().msg, sizeof res[i].msg);
+        } catch (const std::bad_alloc&) {
+            res[i].code = MB200_ENOMEM;
+            snprintf(res[i].msg, sizeof res[i].msg, "host allocation failed");
+        } catch (...) {
+            res[i].code = MB200_ECUDA;
+            snprintf(res[i].msg, sizeof res[i].msg, "unexpected failure on device slot %d", (int)i);
+        }
+    };
+    std::vector<std::thread> th;
+    size_t started = 1;
+    try {
+        for (size_t i = 1; i < ds.size(); ++i) {
+            th.emplace_back(body, i);
+            started = i + 1;
+        }
+    } catch (...) {  // std::system_error: could not spawn; the remaining devices run on this thread
+    }
+    body(0);
+    for (size_t i = started; i < ds.size(); ++i) body(i);
+    for (auto& t : th) t.join();
+    use(*g.devs[0]);
+    for (auto& r : res)
+        if (r.code) {
+            last_error().code = r.code;
+            memcpy(last_error().msg, r.msg, sizeof r.msg);
+            throw Exc{r.code};
+        }
+}
+static std::vector<Device*> all_devices() {
+    std::vector<Device*> v;
+    for (auto& d : g.devs) v.push_back(d.get());
+    return v;
+}
+
+static void destroy_ctxs(Device& d) {
+#ifndef MB200_EMU
+    for (auto& c : d.ctxs)
         if (c.have_stream) {
             cudaStreamSynchronize(c.stream);
             cudaStreamDestroy(c.stream);
             cudaEventDestroy(c.ev_inputs);
+            cudaEventDestroy(c.ev_tail);
             for (int i = 0; i < 3; ++i) {
                 cudaStreamSynchronize(c.side[i]);
                 cudaStreamDestroy(c.side[i]);
                 cudaEventDestroy(c.ev_side[i]);
             }
-            for (int i = 0; i < 4; ++i) {
-                cudaStreamSynchronize(c.tail[i]);
-                cudaStreamDestroy(c.tail[i]);
-                cudaEventDestroy(c.ev_acc[i]);
-            }
-            cudaEventDestroy(c.ev_tail);
         }
 #endif
-    g.ctxs.clear();
-    g.ctxs.resize(n);
+    d.ctxs.clear();
+}
+static void set_ctx_count(Device& d, size_t n) {
+    destroy_ctxs(d);
+    d.ctxs.resize(n);
 #ifndef MB200_EMU
-    // Throughput kernels (copies, NTT, digit sort, bucket accumulation) run on low-priority
-    // streams; the latency-bound tails (bucket reduction, s*A and r*B1, encoding, self-check) on
-    // high-priority ones, so that their few blocks are placed as soon as any SM has room instead
-    // of queueing behind the thousands of pending accumulation blocks of the next chunk.
-    int pr_least = 0, pr_greatest = 0;
-    MB_CUDA(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
-    // measured on B200 (profiles/r01_tail_streams_ab.jsonl): no gain over the single-stream tails,
-    // the accumulation blocks hold the register file either way -- kept as an opt-in experiment
-    const bool split = getenv("MB200_TAIL_STREAMS") != nullptr;
-    for (auto& c : g.ctxs) {
-        MB_CUDA(cudaStreamCreateWithPriority(&c.stream, cudaStreamNonBlocking, pr_least));
+    for (auto& c : d.ctxs) {
+        MB_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         MB_CUDA(cudaEventCreateWithFlags(&c.ev_inputs, cudaEventDisableTiming));
+        MB_CUDA(cudaEventCreateWithFlags(&c.ev_tail, cudaEventDisableTiming));
         for (int i = 0; i < 3; ++i) {
-            MB_CUDA(cudaStreamCreateWithPriority(&c.side[i], cudaStreamNonBlocking, pr_least));
+            MB_CUDA(cudaStreamCreateWithFlags(&c.side[i], cudaStreamNonBlocking));
             MB_CUDA(cudaEventCreateWithFlags(&c.ev_side[i], cudaEventDisableTiming));
         }
-        for (int i = 0; i < 4; ++i) {
-            MB_CUDA(cudaStreamCreateWithPriority(&c.tail[i], cudaStreamNonBlocking, pr_greatest));
-            MB_CUDA(cudaEventCreateWithFlags(&c.ev_acc[i], cudaEventDisableTiming));
-        }
-        MB_CUDA(cudaEventCreateWithFlags(&c.ev_tail, cudaEventDisableTiming));
-        c.split_tail = split;
         c.have_stream = true;
     }
 #endif
@@ -108,33 +178,35 @@ static uint32_t standalone_window(size_t n) {
     return env_u32("MB200_C_MSM", best);
 }
 
+// One MSM over device-resident bases on device `d`; scalars from host memory.  out_dev: one XYZZ on `d`.
 template <class F>
-static void msm_on_device_bases(const Affine<F>* bases, const uint8_t* scalars_host, size_t n, XYZZ<F>* out_dev) {
+static void msm_on_device_bases(Device& d, const Affine<F>* bases, const uint8_t* scalars_host, size_t n, XYZZ<F>* out_dev) {
     if (n == 0) {
-        dev_memset(out_dev, 0, sizeof(XYZZ<F>), g.main);
+        dev_memset(out_dev, 0, sizeof(XYZZ<F>), d.main);
+        stream_sync(d.main);
         return;
     }
     if (n >= (1ull << 31)) fail(MB200_EINVAL, "MSM of %s%ld bases is too large", "", (long)n);
     DevBuf sel(n * 4), pool(n * 32), flag(4);
     IotaArgs ia{n, sel.as<uint32_t>()};
-    launch_iota_kernel(ia, g.main);
-    copy_h2d(pool.p, scalars_host, n * 32, g.main);
-    dev_memset(flag.p, 0, 4, g.main);
+    launch_iota_kernel(ia, d.main);
+    copy_h2d(pool.p, scalars_host, n * 32, d.main);
+    dev_memset(flag.p, 0, 4, d.main);
     ValidateArgs va{n, pool.as<Fr>(), n, n, flag.as<uint32_t>()};
-    launch_validate_scalars(va, g.main);
+    launch_validate_scalars(va, d.main);
     MsmClass k = msm_make_class(bases, sel.as<uint32_t>(), (uint32_t)n, standalone_window(n), false);
-    msm_run<F>(k, 1, pool.as<uint32_t>(), n, out_dev, g.msm, g.main);
+    msm_run<F>(k, 1, pool.as<uint32_t>(), n, out_dev, d.msm, d.main);
     uint32_t bad = 0;
-    copy_d2h(&bad, flag.p, 4, g.main);
-    stream_sync(g.main);
+    copy_d2h(&bad, flag.p, 4, d.main);
+    stream_sync(d.main);
     if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
 }
 
-static NttCache& ntt_cache(unsigned log_n) {
-    auto it = g.ntt.find(log_n);
-    if (it != g.ntt.end()) return *it->second;
-    NttCache* c = new NttCache();
-    c->dom.build(log_n, g.main);
+static NttCache& ntt_cache(Device& d, unsigned log_n) {
+    auto it = d.ntt.find(log_n);
+    if (it != d.ntt.end()) return *it->second;
+    std::unique_ptr<NttCache> c(new NttCache());
+    c->dom.build(log_n, d.main);
     size_t n = (size_t)1 << log_n;
     c->gpow.alloc(n * sizeof(Fr));
     PowArgs pa;
@@ -142,9 +214,10 @@ static NttCache& ntt_cache(unsigned log_n) {
     pa.out = c->gpow.as<Fr>();
     pa.base = fr_from_u64_host(7);
     pa.scale = Fr::one();
-    launch_fr_powers(pa, g.main);
-    g.ntt[log_n] = c;
-    return *c;
+    launch_fr_powers(pa, d.main);
+    NttCache* raw = c.release();
+    d.ntt[log_n] = raw;
+    return *raw;
 }
 
 static void check_scalars_dev(const Fr* base, size_t per_row, size_t row_stride, size_t nrows, uint32_t* flag,
@@ -153,7 +226,7 @@ static void check_scalars_dev(const Fr* base, size_t per_row, size_t row_stride,
     launch_validate_scalars(va, s);
 }
 
-// Buffers a batch needs for its lifetime.  They are recycled across batches: cudaMalloc /
+// Buffers a batch slice needs for its lifetime.  They are recycled across batches: cudaMalloc /
 // cudaFree / cudaFreeHost synchronise the whole device, which would serialise batches that are
 // meant to overlap (submit k+1 while k is still running, wait k while k+1 runs).
 struct TicketRes {
@@ -161,137 +234,217 @@ struct TicketRes {
     size_t staged_cap = 0;
     uint32_t* verdicts = nullptr;  // pinned: per-proof result of the self-check (option "verify")
     size_t verdicts_cap = 0;
-    DevBuf v_a, v_b, v_c, v_in, v_ok;  // self-check inputs / verdicts of this batch (device)
-    DevBuf flag;                   // set by the canonical-scalar checks of this batch
+    DevBuf v_a, v_b, v_c, v_in, v_ok;  // self-check inputs / verdicts of this slice (device)
+    DevBuf flag;                   // set by the canonical-scalar checks of this slice
     ~TicketRes() {
         host_free_pinned(staged);
         host_free_pinned(verdicts);
     }
 };
-static std::vector<TicketRes*> g_res_free;
-static TicketRes* res_acquire() {
-    if (g_res_free.empty()) return new TicketRes();
-    TicketRes* r = g_res_free.back();
-    g_res_free.pop_back();
+static TicketRes* res_acquire(Device& d) {
+    if (d.res_free.empty()) return new TicketRes();
+    TicketRes* r = d.res_free.back();
+    d.res_free.pop_back();
     return r;
 }
 
-// One submitted batch: everything needed to finish it later.
-struct Ticket {
+// The part of a submitted batch that runs on one device: proofs [first, first + count).
+struct Slice {
+    Device* dev = nullptr;
+    size_t first = 0, count = 0;
     TicketRes* res = nullptr;
     uint8_t* staged = nullptr;     // = res->staged
     uint32_t* verdicts = nullptr;  // = res->verdicts when the self-check is on
+    uint32_t* flag = nullptr;      // = res->flag
 #ifndef MB200_EMU
     cudaEvent_t ev_v[4] = {nullptr, nullptr, nullptr, nullptr};
-#endif
-    uint8_t* out = nullptr;     // caller's buffer
-    size_t n_proofs = 0;
-    uint32_t* flag = nullptr;   // = res->flag
-#ifndef MB200_EMU
     cudaEvent_t ev0 = nullptr;
     std::vector<cudaEvent_t> ev1;
 #endif
 };
+// One submitted batch: everything needed to finish it later.
+struct Ticket {
+    std::vector<Slice> slices;
+    uint8_t* out = nullptr;  // caller's buffer
+    size_t n_proofs = 0;
+    int verify = 0;          // option "verify" as it was at submit time
+};
 static std::map<uint64_t, Ticket*> g_tickets;
 static uint64_t g_next_ticket = 1;
-static size_t g_next_ctx = 0;  // chunks go round the contexts across batches, so consecutive batches overlap
 
+static void slice_release(Slice& sl) {
+#ifndef MB200_EMU
+    if (sl.ev0) cudaEventDestroy(sl.ev0);
+    for (auto& e : sl.ev_v)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : sl.ev1)
+        if (e) cudaEventDestroy(e);
+    sl.ev0 = nullptr;
+    sl.ev1.clear();
+    for (auto& e : sl.ev_v) e = nullptr;
+#endif
+    if (sl.res) sl.dev->res_free.push_back(sl.res);
+    sl.res = nullptr;
+}
 static void ticket_destroy(Ticket* t) {
     if (!t) return;
-#ifndef MB200_EMU
-    if (t->ev0) cudaEventDestroy(t->ev0);
-    for (auto& e : t->ev_v)
-        if (e) cudaEventDestroy(e);
-    for (auto& e : t->ev1)
-        if (e) cudaEventDestroy(e);
-#endif
-    if (t->res) g_res_free.push_back(t->res);
+    for (auto& sl : t->slices) slice_release(sl);
     delete t;
 }
 
-// Enqueue a whole batch on the chunk contexts; no host synchronisation.
-static uint64_t prove_submit(const Params& P, size_t n_proofs, size_t rows, const ProveInputs& in, uint8_t* proofs_out) {
+// How a batch is cut over the devices: whole chunks, contiguous, as even as the chunk size
+// allows; a batch of fewer chunks than devices uses that many devices, starting at a rotating
+// slot so that small batches submitted back to back land on different GPUs.
+static std::vector<Slice> plan_slices(size_t n_proofs) {
+    const size_t nd = g.devs.size(), chunk = g.chunk;
+    const size_t units = (n_proofs + chunk - 1) / chunk;
+    const size_t used = std::min(nd, units);
+    std::vector<Slice> out;
+    size_t first = 0;
+    for (size_t k = 0; k < used; ++k) {
+        size_t u = units / used + (k < units % used ? 1 : 0);
+        size_t count = std::min(u * chunk, n_proofs - first);
+        Slice sl;
+        sl.dev = g.devs[(g.next_dev + k) % nd].get();
+        sl.first = first;
+        sl.count = count;
+        out.push_back(sl);
+        first += count;
+    }
+    g.next_dev = (g.next_dev + used) % nd;
+    return out;
+}
+
+// Enqueue one slice on its device's chunk contexts; no host synchronisation (with pinned inputs).
+static void slice_submit(const Params& P, Slice& sl, int verify, size_t rows, const ProveInputs& in) {
+    Device& d = *sl.dev;
+    TicketRes* R = sl.res = res_acquire(d);
+    if (R->staged_cap < sl.count * 192) {
+        host_free_pinned(R->staged);
+        R->staged = nullptr;
+        R->staged_cap = 0;
+        R->staged = (uint8_t*)host_alloc_pinned(sl.count * 192);
+        R->staged_cap = sl.count * 192;
+    }
+    sl.staged = R->staged;
+    VerifySink sink;
+    if (verify) {
+        if (R->verdicts_cap < sl.count * 4) {
+            host_free_pinned(R->verdicts);
+            R->verdicts = nullptr;
+            R->verdicts_cap = 0;
+            R->verdicts = (uint32_t*)host_alloc_pinned(sl.count * 4);
+            R->verdicts_cap = sl.count * 4;
+        }
+        sl.verdicts = R->verdicts;
+        R->v_a.ensure(sl.count * sizeof(G1Affine));
+        R->v_b.ensure(sl.count * sizeof(G2Affine));
+        R->v_c.ensure(sl.count * sizeof(G1Affine));
+        R->v_in.ensure(sl.count * (size_t)P.n_inputs * 32);
+        R->v_ok.ensure(sl.count * 4);
+        sink.a = R->v_a.as<G1Affine>();
+        sink.b = R->v_b.as<G2Affine>();
+        sink.c = R->v_c.as<G1Affine>();
+        sink.inputs = R->v_in.as<uint32_t>();
+        sink.ok_dev = R->v_ok.as<uint32_t>();
+        sink.ok_host = sl.verdicts;
+    }
+    R->flag.ensure(4);
+    sl.flag = R->flag.as<uint32_t>();
+    dev_memset(sl.flag, 0, 4, d.main);
+#ifndef MB200_EMU
+    // every chunk stream starts after `ev0` (and so after the flag reset)
+    sl.ev1.assign(d.ctxs.size(), nullptr);
+    MB_CUDA(cudaEventCreate(&sl.ev0));
+    for (auto& e : sl.ev1) MB_CUDA(cudaEventCreate(&e));
+    MB_CUDA(cudaEventRecord(sl.ev0, d.main));
+    for (auto& x : d.ctxs) MB_CUDA(cudaStreamWaitEvent(x.stream, sl.ev0, 0));
+#endif
+    // the slice's view of the caller's buffers; chunk offsets below are relative to the slice
+    ProveInputs sin = in;
+    const size_t rb = rows * 32;
+    if (in.a) {
+        sin.a = in.a + sl.first * rb;
+        sin.b = in.b + sl.first * rb;
+        sin.c = in.c + sl.first * rb;
+    }
+    sin.inputs = in.inputs + sl.first * (size_t)P.n_inputs * 32;
+    sin.aux = in.aux + sl.first * (size_t)P.n_aux * 32;
+    sin.r = in.r + sl.first * 32;
+    sin.s = in.s + sl.first * 32;
+    for (size_t first = 0; first < sl.count; first += g.chunk) {
+        uint32_t count = (uint32_t)std::min<size_t>(g.chunk, sl.count - first);
+        ProveCtx& x = d.ctxs[d.next_ctx++ % d.ctxs.size()];
+#ifndef MB200_EMU
+        sink.stream = d.vstream[d.next_v++ % 4];
+#endif
+        prove_chunk(P, x, sin, first, count, rows, sl.staged, sink);
+        // canonical-scalar check on what was just staged (abc and aux..s of the pool)
+        check_scalars_dev(x.abc.as<Fr>(), (size_t)count * 3 * rows, 0, 1, sl.flag, x.stream);
+        check_scalars_dev(x.pool.as<Fr>() + P.idx_aux, P.idx_one - P.idx_aux, P.pool_stride, count, sl.flag, x.stream);
+    }
+#ifndef MB200_EMU
+    for (size_t i = 0; i < d.ctxs.size(); ++i) MB_CUDA(cudaEventRecord(sl.ev1[i], d.ctxs[i].stream));
+    if (verify)
+        for (int i = 0; i < 4; ++i) {
+            MB_CUDA(cudaEventCreateWithFlags(&sl.ev_v[i], cudaEventDisableTiming));
+            MB_CUDA(cudaEventRecord(sl.ev_v[i], d.vstream[i]));
+        }
+#endif
+}
+
+// Enqueue a whole batch: one slice per device, each enqueued by its own host thread.
+static uint64_t prove_submit(const std::vector<Params*>& reps, size_t n_proofs, size_t rows, const ProveInputs& in,
+                             uint8_t* proofs_out) {
     require_init();
+    const Params& P0 = *reps[0];
     if (!in.inputs || !in.aux || !in.r || !in.s || !proofs_out) fail(MB200_EINVAL, "null buffer%s", "");
     if (!in.a && !in.b && !in.c) {  // witness-only: rows come from the bound circuit
-        if (!P.r1cs.bound) fail(MB200_EINVAL, "no circuit bound to these parameters%s", "");
-        if (rows != (size_t)P.r1cs.ncons + P.n_inputs) fail(MB200_EINVAL, "rows do not match the bound circuit%s", "");
+        if (!P0.r1cs.bound) fail(MB200_EINVAL, "no circuit bound to these parameters%s", "");
+        if (rows != (size_t)P0.r1cs.ncons + P0.n_inputs) fail(MB200_EINVAL, "rows do not match the bound circuit%s", "");
     } else if (!in.a || !in.b || !in.c) {
         fail(MB200_EINVAL, "null buffer%s", "");
     }
     size_t m = 1;
     while (m < rows) m <<= 1;
-    if (rows == 0 || m != P.m)
-        fail(MB200_EINVAL, "rows does not match the key's domain%s (key m = %ld)", "", (long)P.m);
+    if (rows == 0 || m != P0.m)
+        fail(MB200_EINVAL, "rows does not match the key's domain%s (key m = %ld)", "", (long)P0.m);
     Ticket* t = new Ticket();
     try {
         t->n_proofs = n_proofs;
         t->out = proofs_out;
-        TicketRes* R = t->res = res_acquire();
-        if (R->staged_cap < n_proofs * 192) {
-            host_free_pinned(R->staged);
-            R->staged = nullptr;
-            R->staged = (uint8_t*)host_alloc_pinned(n_proofs * 192);
-            R->staged_cap = n_proofs * 192;
-        }
-        t->staged = R->staged;
-        VerifySink sink;
-        if (g.verify) {
-            if (R->verdicts_cap < n_proofs * 4) {
-                host_free_pinned(R->verdicts);
-                R->verdicts = nullptr;
-                R->verdicts = (uint32_t*)host_alloc_pinned(n_proofs * 4);
-                R->verdicts_cap = n_proofs * 4;
-            }
-            t->verdicts = R->verdicts;
-            R->v_a.ensure(n_proofs * sizeof(G1Affine));
-            R->v_b.ensure(n_proofs * sizeof(G2Affine));
-            R->v_c.ensure(n_proofs * sizeof(G1Affine));
-            R->v_in.ensure(n_proofs * (size_t)P.n_inputs * 32);
-            R->v_ok.ensure(n_proofs * 4);
-            sink.a = R->v_a.as<G1Affine>();
-            sink.b = R->v_b.as<G2Affine>();
-            sink.c = R->v_c.as<G1Affine>();
-            sink.inputs = R->v_in.as<uint32_t>();
-            sink.ok_dev = R->v_ok.as<uint32_t>();
-            sink.ok_host = t->verdicts;
-        }
-        R->flag.ensure(4);
-        t->flag = R->flag.as<uint32_t>();
-        dev_memset(t->flag, 0, 4, g.main);
+        t->verify = g.verify;
+        if (in.on_device) {  // the inputs are on the caller's current device: the whole batch runs there
+            Slice sl;
+            sl.dev = g.devs[0].get();
 #ifndef MB200_EMU
-        // every chunk stream starts after `ev0` (and so after the flag reset)
-        t->ev1.assign(g.ctxs.size(), nullptr);
-        MB_CUDA(cudaEventCreate(&t->ev0));
-        for (auto& e : t->ev1) MB_CUDA(cudaEventCreate(&e));
-        MB_CUDA(cudaEventRecord(t->ev0, g.main));
-        for (auto& x : g.ctxs) MB_CUDA(cudaStreamWaitEvent(x.stream, t->ev0, 0));
+            int cur = 0;
+            MB_CUDA(cudaGetDevice(&cur));
+            for (auto& d : g.devs)
+                if (d->id == cur) sl.dev = d.get();
 #endif
-        for (size_t first = 0; first < n_proofs; first += g.chunk) {
-            uint32_t count = (uint32_t)std::min<size_t>(g.chunk, n_proofs - first);
-            ProveCtx& x = g.ctxs[g_next_ctx++ % g.ctxs.size()];
-#ifndef MB200_EMU
-            sink.stream = g.vstream[g.next_v++ % 4];
-#endif
-            prove_chunk(P, x, in, first, count, rows, t->staged, sink);
-            // canonical-scalar check on what was just staged (abc and aux..s of the pool)
-            check_scalars_dev(x.abc.as<Fr>(), (size_t)count * 3 * rows, 0, 1, t->flag, x.stream);
-            check_scalars_dev(x.pool.as<Fr>() + P.idx_aux, P.idx_one - P.idx_aux, P.pool_stride, count,
-                              t->flag, x.stream);
+            sl.first = 0;
+            sl.count = n_proofs;
+            t->slices.push_back(sl);
+        } else {
+            t->slices = plan_slices(n_proofs);
         }
-#ifndef MB200_EMU
-        for (size_t i = 0; i < g.ctxs.size(); ++i) MB_CUDA(cudaEventRecord(t->ev1[i], g.ctxs[i].stream));
-        if (g.verify)
-            for (int i = 0; i < 4; ++i) {
-                MB_CUDA(cudaEventCreateWithFlags(&t->ev_v[i], cudaEventDisableTiming));
-                MB_CUDA(cudaEventRecord(t->ev_v[i], g.vstream[i]));
-            }
-#endif
+        std::vector<Device*> ds;
+        for (auto& sl : t->slices) ds.push_back(sl.dev);
+        const int verify = t->verify;
+        for_devices(ds, [&](Device& d) {
+            for (auto& sl : t->slices)
+                if (sl.dev == &d) slice_submit(*reps[d.slot], sl, verify, rows, in);
+        });
     } catch (...) {
-#ifndef MB200_EMU
         // nothing of this batch may still be running when its buffers go back to the pool
-        for (auto& x : g.ctxs) cudaStreamSynchronize(x.stream);
-        for (auto& v : g.vstream) cudaStreamSynchronize(v);
+#ifndef MB200_EMU
+        for (auto& sl : t->slices) {
+            cudaSetDevice(sl.dev->id);
+            for (auto& x : sl.dev->ctxs) cudaStreamSynchronize(x.stream);
+            for (auto& v : sl.dev->vstream) cudaStreamSynchronize(v);
+        }
+        cudaSetDevice(g.devs[0]->id);
 #endif
         ticket_destroy(t);
         throw;
@@ -301,41 +454,59 @@ static uint64_t prove_submit(const Params& P, size_t n_proofs, size_t rows, cons
     return id;
 }
 
-// Wait for a submitted batch, check its flag, hand the proofs to the caller.
+// Wait for a submitted batch, check its flags, hand the proofs to the caller.
 static void prove_wait(uint64_t id) {
     auto it = g_tickets.find(id);
     if (it == g_tickets.end()) fail(MB200_EINVAL, "unknown ticket%s (%ld)", "", (long)id);
     Ticket* t = it->second;
     g_tickets.erase(it);
-    uint32_t bad = 0;
     try {
-#ifndef MB200_EMU
         g.last_batch_ms = 0;
-        for (auto& e : t->ev1) {
-            MB_CUDA(cudaEventSynchronize(e));
-            float ms = 0;
-            MB_CUDA(cudaEventElapsedTime(&ms, t->ev0, e));
-            if (ms > g.last_batch_ms) g.last_batch_ms = ms;
-        }
-#endif
+        uint32_t bad = 0;
+        for (auto& sl : t->slices) {
+            Device& d = *sl.dev;
+            use(d);
 #ifndef MB200_EMU
-        for (auto& e : t->ev_v)
-            if (e) MB_CUDA(cudaEventSynchronize(e));
-#endif
-        copy_d2h(&bad, t->flag, 4, g.main);
-        stream_sync(g.main);
-        if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
-        memcpy(t->out, t->staged, t->n_proofs * 192);
-        if (t->verdicts)
-            for (size_t i = 0; i < t->n_proofs; ++i) {
-                g.verified++;
-                if (!t->verdicts[i]) {
-                    g.verify_failed++;
-                    if (g.verify == 1)
-                        fail(MB200_EVERIFY, "proof %s%ld does not satisfy the verification equation", "", (long)i);
-                }
+            for (auto& e : sl.ev1) {
+                MB_CUDA(cudaEventSynchronize(e));
+                float ms = 0;
+                MB_CUDA(cudaEventElapsedTime(&ms, sl.ev0, e));
+                if (ms > g.last_batch_ms) g.last_batch_ms = ms;
             }
+            for (auto& e : sl.ev_v)
+                if (e) MB_CUDA(cudaEventSynchronize(e));
+#endif
+            uint32_t b = 0;
+            copy_d2h(&b, sl.flag, 4, d.main);
+            stream_sync(d.main);
+            bad |= b;
+        }
+        use(*g.devs[0]);
+        if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
+        for (auto& sl : t->slices) memcpy(t->out + sl.first * 192, sl.staged, sl.count * 192);
+        for (auto& sl : t->slices)
+            if (sl.verdicts)
+                for (size_t i = 0; i < sl.count; ++i) {
+                    g.verified++;
+                    if (!sl.verdicts[i]) {
+                        g.verify_failed++;
+                        if (t->verify == 1)
+                            fail(MB200_EVERIFY, "proof %s%ld does not satisfy the verification equation", "",
+                                 (long)(sl.first + i));
+                    }
+                }
     } catch (...) {
+#ifndef MB200_EMU
+        // a failed wait must not hand buffers back while later slices are still running
+        for (auto& sl : t->slices) {
+            cudaSetDevice(sl.dev->id);
+            for (auto& e : sl.ev1)
+                if (e) cudaEventSynchronize(e);
+            for (auto& e : sl.ev_v)
+                if (e) cudaEventSynchronize(e);
+        }
+        cudaSetDevice(g.devs[0]->id);
+#endif
         ticket_destroy(t);
         throw;
     }
@@ -344,7 +515,7 @@ static void prove_wait(uint64_t id) {
 
 // CSR matrices of a recorded circuit -> device, columns rewritten to scalar-pool
 // indices, coefficients interned into a dictionary (Montgomery form; 0 -> +1, 1 -> -1).
-static void r1cs_upload(R1csDev& R, const mb200_circuit& c, size_t idx_aux, size_t idx_inputs) {
+static void r1cs_upload(Device& d, R1csDev& R, const mb200_circuit& c, size_t idx_aux, size_t idx_inputs) {
     std::map<std::array<uint64_t, 4>, uint32_t> dict;
     std::vector<mbh::Fr> dict_vals;
     auto intern = [&](const mbh::Fr& f) {
@@ -370,10 +541,10 @@ static void r1cs_upload(R1csDev& R, const mb200_circuit& c, size_t idx_aux, size
         R.rowptr[k].alloc(M.rowptr.size() * 4);
         R.col[k].alloc(col.size() * 4);
         R.cidx[k].alloc(cidx.size() * 4);
-        copy_h2d(R.rowptr[k].p, M.rowptr.data(), M.rowptr.size() * 4, g.main);
-        copy_h2d(R.col[k].p, col.data(), col.size() * 4, g.main);
-        copy_h2d(R.cidx[k].p, cidx.data(), cidx.size() * 4, g.main);
-        stream_sync(g.main);  // the staging vectors die at the end of this iteration
+        copy_h2d(R.rowptr[k].p, M.rowptr.data(), M.rowptr.size() * 4, d.main);
+        copy_h2d(R.col[k].p, col.data(), col.size() * 4, d.main);
+        copy_h2d(R.cidx[k].p, cidx.data(), cidx.size() * 4, d.main);
+        stream_sync(d.main);  // the staging vectors die at the end of this iteration
     }
     {  // rows by descending total non-zero count (stable: equal rows stay in constraint order)
         std::vector<uint32_t> order(c.n_constraints);
@@ -384,23 +555,24 @@ static void r1cs_upload(R1csDev& R, const mb200_circuit& c, size_t idx_aux, size
         };
         std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return cost(x) > cost(y); });
         R.order.alloc(order.size() * 4 + 4);
-        copy_h2d(R.order.p, order.data(), order.size() * 4, g.main);
-        stream_sync(g.main);
+        copy_h2d(R.order.p, order.data(), order.size() * 4, d.main);
+        stream_sync(d.main);
     }
     // mbh::Fr (4 x u64 Montgomery, R = 2^256) has the same memory image as the device Fr (8 x u32)
     R.dict.alloc(dict_vals.size() * 32);
-    copy_h2d(R.dict.p, dict_vals.data(), dict_vals.size() * 32, g.main);
-    stream_sync(g.main);
+    copy_h2d(R.dict.p, dict_vals.data(), dict_vals.size() * 32, d.main);
+    stream_sync(d.main);
     R.ncons = c.n_constraints;
     R.n_inputs = c.n_inputs;
     R.n_aux = c.n_aux;
     R.bound = true;
 }
 
-static int prove_impl(const Params& P, size_t n_proofs, size_t rows, const ProveInputs& in, uint8_t* proofs_out) {
+static int prove_impl(const std::vector<Params*>& reps, size_t n_proofs, size_t rows, const ProveInputs& in,
+                      uint8_t* proofs_out) {
     require_init();
     if (n_proofs == 0) return MB200_OK;
-    prove_wait(prove_submit(P, n_proofs, rows, in, proofs_out));
+    prove_wait(prove_submit(reps, n_proofs, rows, in, proofs_out));
     return MB200_OK;
 }
 
@@ -422,56 +594,136 @@ using namespace mb;
     return MB200_OK;
 
 struct mb200_params {
-    Params* p;
+    std::vector<Params*> rep;  // one replica per opened device, indexed by Device::slot
+    const Params& p0() const { return *rep[0]; }
 };
+static void params_destroy(mb200_params* p) {
+    if (!p) return;
+    for (size_t i = 0; i < p->rep.size(); ++i)
+        if (p->rep[i]) {
+#ifndef MB200_EMU
+            if (i < g.devs.size()) {
+                cudaSetDevice(g.devs[i]->id);
+                cudaDeviceSynchronize();
+            }
+#endif
+            delete p->rep[i];
+        }
+#ifndef MB200_EMU
+    if (!g.devs.empty()) cudaSetDevice(g.devs[0]->id);
+#endif
+    delete p;
+}
+static const std::vector<Params*>& replicas(const mb200_params* p) {
+    if (!p || p->rep.empty() || !p->rep[0]) fail(MB200_EINVAL, "null parameters%s", "");
+    if (p->rep.size() != g.devs.size()) fail(MB200_ESTATE, "parameters were loaded under a different mb200_init%s", "");
+    return p->rep;
+}
 
 extern "C" {
 
 int mb200_init(const int* device_ids, int n_devices) {
     MB_API_BEGIN
     if (g.inited) return MB200_OK;
+    std::vector<int> ids;
 #ifndef MB200_EMU
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
         fail(MB200_ECUDA, "no CUDA device: %s (this library has no CPU path)", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
-    int dev = 0;
-    if (device_ids && n_devices > 0) dev = device_ids[0];
-    else MB_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= count) fail(MB200_EINVAL, "device id out of range%s (%ld)", "", (long)dev);
-    MB_CUDA(cudaSetDevice(dev));
-    cudaDeviceProp prop;
-    MB_CUDA(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major < 10) fail(MB200_ECUDA, "device %s is not sm_100 (compute capability %ld.x)", prop.name, (long)prop.major);
-    g.device = dev;
-    MB_CUDA(cudaStreamCreateWithFlags(&g.main, cudaStreamNonBlocking));
-    for (auto& v : g.vstream) MB_CUDA(cudaStreamCreateWithFlags(&v, cudaStreamNonBlocking));
+    if (device_ids && n_devices > 0) {
+        ids.assign(device_ids, device_ids + n_devices);
+    } else if (n_devices < 0) {  // every visible device
+        for (int i = 0; i < count; ++i) ids.push_back(i);
+    } else {
+        int dev = 0;
+        MB_CUDA(cudaGetDevice(&dev));
+        ids.push_back(dev);
+    }
+    if (ids.size() > 64) fail(MB200_EINVAL, "too many devices%s (%ld)", "", (long)ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) {
+        if (ids[i] < 0 || ids[i] >= count) fail(MB200_EINVAL, "device id out of range%s (%ld)", "", (long)ids[i]);
+        for (size_t j = 0; j < i; ++j)
+            if (ids[j] == ids[i]) fail(MB200_EINVAL, "device id listed twice%s (%ld)", "", (long)ids[i]);
+        cudaDeviceProp prop;
+        MB_CUDA(cudaGetDeviceProperties(&prop, ids[i]));
+        if (prop.major < 10) fail(MB200_ECUDA, "device %s is not sm_100 (compute capability %ld.x)", prop.name, (long)prop.major);
+    }
 #else
-    (void)device_ids;
-    (void)n_devices;
+    // host emulation (tests only): "devices" are separate bookkeeping over the same host memory
+    int n = (device_ids && n_devices > 0) ? n_devices : 1;
+    if (n > 64) fail(MB200_EINVAL, "too many devices%s (%ld)", "", (long)n);
+    for (int i = 0; i < n; ++i) ids.push_back(i);
 #endif
     g.chunk = env_u32("MB200_CHUNK", 64);
-    set_ctx_count(env_u32("MB200_STREAMS", 3));
+    g.n_streams = env_u32("MB200_STREAMS", 3);
+    if (g.n_streams < 1 || g.n_streams > 8) g.n_streams = 3;
+    try {
+        for (size_t i = 0; i < ids.size(); ++i) {
+            std::unique_ptr<Device> d(new Device());
+            d->id = ids[i];
+            d->slot = (int)i;
+            g.devs.push_back(std::move(d));
+        }
+        for (auto& dp : g.devs) {
+            Device& d = *dp;
+            use(d);
+#ifndef MB200_EMU
+            MB_CUDA(cudaStreamCreateWithFlags(&d.main, cudaStreamNonBlocking));
+            for (auto& v : d.vstream) MB_CUDA(cudaStreamCreateWithFlags(&v, cudaStreamNonBlocking));
+#endif
+            set_ctx_count(d, g.n_streams);
+        }
+#ifndef MB200_EMU
+        // K6 (partials of a base-split MSM travel GPU -> GPU): let slot 0 be written by its peers
+        for (size_t i = 1; i < g.devs.size(); ++i) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, g.devs[i]->id, g.devs[0]->id);
+            if (can) {
+                cudaSetDevice(g.devs[i]->id);
+                cudaError_t pe = cudaDeviceEnablePeerAccess(g.devs[0]->id, 0);
+                if (pe != cudaSuccess) cudaGetLastError();  // already enabled, or unsupported: cudaMemcpyPeerAsync still works
+            }
+        }
+#endif
+        use(*g.devs[0]);
+    } catch (...) {
+        g.devs.clear();
+        throw;
+    }
     g.inited = true;
     MB_API_END
+}
+
+int mb200_device_count(void) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    return g.inited ? (int)g.devs.size() : 0;
 }
 
 int mb200_shutdown(void) {
     MB_API_BEGIN
     if (!g.inited) return MB200_OK;
-    for (auto& kv : g.ntt) delete kv.second;
-    g.ntt.clear();
-    set_ctx_count(0);
-    for (auto* r : g_res_free) delete r;
-    g_res_free.clear();
-    g.msm = MsmScratch();
+    for (auto& kv : g_tickets) ticket_destroy(kv.second);  // batches never waited for
+    g_tickets.clear();
+    for (auto& dp : g.devs) {
+        Device& d = *dp;
 #ifndef MB200_EMU
-    cudaStreamDestroy(g.main);
-    for (auto& v : g.vstream) {
-        cudaStreamSynchronize(v);
-        cudaStreamDestroy(v);
-    }
+        cudaSetDevice(d.id);
+        cudaDeviceSynchronize();
 #endif
+        for (auto& kv : d.ntt) delete kv.second;
+        d.ntt.clear();
+        destroy_ctxs(d);
+        for (auto* r : d.res_free) delete r;
+        d.res_free.clear();
+        d.msm = MsmScratch();
+        d.peer_parts.release();
+#ifndef MB200_EMU
+        cudaStreamDestroy(d.main);
+        for (auto& v : d.vstream) cudaStreamDestroy(v);
+#endif
+    }
+    g.devs.clear();
     g.inited = false;
     MB_API_END
 }
@@ -482,15 +734,20 @@ int mb200_params_load(const uint8_t* bytes, size_t len, const uint8_t* a_aux_den
     require_init();
     if (!out) fail(MB200_EINVAL, "null out pointer%s", "");
     *out = nullptr;
-    Params* p = params_load(bytes, len, a_aux_density, b_input_density, b_aux_density, g.main);
-    *out = new mb200_params{p};
+    std::unique_ptr<mb200_params, void (*)(mb200_params*)> p(new mb200_params(), params_destroy);
+    p->rep.assign(g.devs.size(), nullptr);
+    // replicate: every device ingests the bytes and expands its own window tables, in parallel
+    for_devices(all_devices(), [&](Device& d) {
+        p->rep[d.slot] = params_load(bytes, len, a_aux_density, b_input_density, b_aux_density, d.main);
+    });
+    *out = p.release();
     MB_API_END
 }
 
 int mb200_params_info(const mb200_params* p, uint64_t info[10]) {
     MB_API_BEGIN
-    if (!p || !p->p || !info) fail(MB200_EINVAL, "null argument%s", "");
-    const Params& P = *p->p;
+    if (!p || p->rep.empty() || !p->rep[0] || !info) fail(MB200_EINVAL, "null argument%s", "");
+    const Params& P = p->p0();
     info[0] = P.n_inputs; info[1] = P.n_aux; info[2] = P.h_len; info[3] = P.a_len; info[4] = P.b_len;
     info[5] = P.m; info[6] = P.consumed; info[7] = P.table_bytes; info[8] = P.k_hl.c; info[9] = P.k_a.c;
     MB_API_END
@@ -498,12 +755,7 @@ int mb200_params_info(const mb200_params* p, uint64_t info[10]) {
 
 void mb200_params_free(mb200_params* p) {
     std::lock_guard<std::mutex> lk(g.mu);
-    if (!p) return;
-#ifndef MB200_EMU
-    cudaDeviceSynchronize();
-#endif
-    delete p->p;
-    delete p;
+    params_destroy(p);
 }
 
 size_t mb200_params_synth_size(uint32_t n_inputs, uint32_t h_len, uint32_t l_len, uint32_t a_len, uint32_t b_len) {
@@ -513,33 +765,33 @@ size_t mb200_params_synth_size(uint32_t n_inputs, uint32_t h_len, uint32_t l_len
 int mb200_params_synthesize(uint64_t seed, uint32_t n_inputs, uint32_t h_len, uint32_t l_len, uint32_t a_len,
                             uint32_t b_len, uint8_t* out, size_t out_len) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     size_t need = params_synth_size(n_inputs, h_len, l_len, a_len, b_len);
     if (!out || out_len < need) fail(MB200_EINVAL, "output buffer too small%s (need %ld bytes)", "", (long)need);
-    DevBuf d(need);
-    params_synthesize(seed, n_inputs, h_len, l_len, a_len, b_len, d.as<uint8_t>(), g.main);
-    copy_d2h(out, d.p, need, g.main);
-    stream_sync(g.main);
+    DevBuf buf(need);
+    params_synthesize(seed, n_inputs, h_len, l_len, a_len, b_len, buf.as<uint8_t>(), d.main);
+    copy_d2h(out, buf.p, need, d.main);
+    stream_sync(d.main);
     MB_API_END
 }
 
 int mb200_synth_points(uint64_t seed, uint32_t stream, uint64_t start, size_t n, int group, uint8_t* out) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if (!out || (group != 1 && group != 2)) fail(MB200_EINVAL, "bad argument%s", "");
     size_t bytes = n * (group == 1 ? 96 : 192);
-    DevBuf d(bytes);
+    DevBuf buf(bytes);
     SynthArgs a;
     a.nthreads = n;
     a.key = stream_key(seed, stream);
     a.start = start;
-    a.out = d.as<uint8_t>();
+    a.out = buf.as<uint8_t>();
     a.g1 = g1_generator_host();
     a.g2 = g2_generator_host();
-    if (group == 1) launch_synth_g1(a, g.main);
-    else launch_synth_g2(a, g.main);
-    copy_d2h(out, d.p, bytes, g.main);
-    stream_sync(g.main);
+    if (group == 1) launch_synth_g1(a, d.main);
+    else launch_synth_g2(a, d.main);
+    copy_d2h(out, buf.p, bytes, d.main);
+    stream_sync(d.main);
     MB_API_END
 }
 
@@ -547,9 +799,9 @@ int mb200_prove_batch(const mb200_params* p, size_t n_proofs, size_t rows, const
                       const uint8_t* b_evals, const uint8_t* c_evals, const uint8_t* inputs, const uint8_t* aux,
                       const uint8_t* r, const uint8_t* s, uint8_t* proofs_out) {
     MB_API_BEGIN
-    if (!p || !p->p) fail(MB200_EINVAL, "null parameters%s", "");
+    require_init();
     ProveInputs in{a_evals, b_evals, c_evals, inputs, aux, r, s, false};
-    return prove_impl(*p->p, n_proofs, rows, in, proofs_out);
+    return prove_impl(replicas(p), n_proofs, rows, in, proofs_out);
     MB_API_END
 }
 
@@ -557,10 +809,10 @@ int mb200_prove_batch_device(const mb200_params* p, size_t n_proofs, size_t rows
                              const void* b_evals, const void* c_evals, const void* inputs, const void* aux,
                              const void* r, const void* s, uint8_t* proofs_out) {
     MB_API_BEGIN
-    if (!p || !p->p) fail(MB200_EINVAL, "null parameters%s", "");
+    require_init();
     ProveInputs in{(const uint8_t*)a_evals, (const uint8_t*)b_evals, (const uint8_t*)c_evals, (const uint8_t*)inputs,
                    (const uint8_t*)aux, (const uint8_t*)r, (const uint8_t*)s, true};
-    return prove_impl(*p->p, n_proofs, rows, in, proofs_out);
+    return prove_impl(replicas(p), n_proofs, rows, in, proofs_out);
     MB_API_END
 }
 
@@ -568,45 +820,56 @@ int mb200_prove_submit(const mb200_params* p, size_t n_proofs, size_t rows, cons
                        const void* c_evals, const void* inputs, const void* aux, const void* r, const void* s,
                        int on_device, uint8_t* proofs_out, uint64_t* ticket) {
     MB_API_BEGIN
-    if (!p || !p->p || !ticket || n_proofs == 0) fail(MB200_EINVAL, "bad argument%s", "");
+    require_init();
+    if (!ticket || n_proofs == 0) fail(MB200_EINVAL, "bad argument%s", "");
     ProveInputs in{(const uint8_t*)a_evals, (const uint8_t*)b_evals, (const uint8_t*)c_evals, (const uint8_t*)inputs,
                    (const uint8_t*)aux, (const uint8_t*)r, (const uint8_t*)s, on_device != 0};
-    *ticket = prove_submit(*p->p, n_proofs, rows, in, proofs_out);
+    *ticket = prove_submit(replicas(p), n_proofs, rows, in, proofs_out);
     MB_API_END
 }
 
 int mb200_params_bind_circuit(mb200_params* p, const mb200_circuit* c) {
     MB_API_BEGIN
     require_init();
-    if (!p || !p->p || !c) fail(MB200_EINVAL, "null argument%s", "");
-    Params& P = *p->p;
+    if (!c) fail(MB200_EINVAL, "null argument%s", "");
+    const std::vector<Params*>& reps = replicas(p);
+    const Params& P = *reps[0];
     if (P.n_inputs != c->n_inputs || P.n_aux != c->n_aux)
         fail(MB200_EINVAL, "circuit and key disagree on the variable counts%s", "");
     if (P.a_len != c->n_inputs + c->a_aux_ones || P.b_len != c->b_input_ones + c->b_aux_ones)
         fail(MB200_EINVAL, "circuit densities do not match the key's query lengths%s", "");
+    // equal counts are not enough: the key's base <-> variable maps were built from the bitmaps it
+    // was loaded with, and a circuit with other positions would give silently wrong proofs
+    if (!density_equal(P.a_aux_density, c->a_aux_density, c->n_aux) ||
+        !density_equal(P.b_input_density, c->b_input_density, c->n_inputs) ||
+        !density_equal(P.b_aux_density, c->b_aux_density, c->n_aux))
+        fail(MB200_EINVAL, "the key was loaded with density bitmaps that are not this circuit's%s", "");
     size_t m = 1;
     while (m < (size_t)c->n_constraints + c->n_inputs) m <<= 1;
     if (m != P.m) fail(MB200_EINVAL, "circuit size does not match the key's domain%s", "");
-    r1cs_upload(P.r1cs, *c, P.idx_aux, P.idx_inputs);
+    for_devices(all_devices(), [&](Device& d) {
+        Params& Pd = *reps[d.slot];
+        r1cs_upload(d, Pd.r1cs, *c, Pd.idx_aux, Pd.idx_inputs);
+    });
     MB_API_END
 }
 
 int mb200_circuit_rows(const mb200_circuit* c, size_t n, const uint8_t* inputs, const uint8_t* aux, uint8_t* a_out,
                        uint8_t* b_out, uint8_t* c_out) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if (!c || (n && (!inputs || !aux || !a_out || !b_out || !c_out))) fail(MB200_EINVAL, "null argument%s", "");
     if (n == 0) return MB200_OK;
     R1csDev R;
-    r1cs_upload(R, *c, 0, c->n_aux);
+    r1cs_upload(d, R, *c, 0, c->n_aux);
     const size_t stride = (size_t)c->n_aux + c->n_inputs, rows = (size_t)c->n_constraints + c->n_inputs;
     DevBuf pool(n * stride * 32), abc(n * 3 * rows * 32), flag(4);
-    dev_memset(flag.p, 0, 4, g.main);
+    dev_memset(flag.p, 0, 4, d.main);
     uint8_t* pl = pool.as<uint8_t>();
-    copy_rows(pl, stride * 32, aux, (size_t)c->n_aux * 32, (size_t)c->n_aux * 32, n, false, g.main);
+    copy_rows(pl, stride * 32, aux, (size_t)c->n_aux * 32, (size_t)c->n_aux * 32, n, false, d.main);
     copy_rows(pl + (size_t)c->n_aux * 32, stride * 32, inputs, (size_t)c->n_inputs * 32, (size_t)c->n_inputs * 32, n, false,
-              g.main);
-    check_scalars_dev(pool.as<Fr>(), n * stride, 0, 1, flag.as<uint32_t>(), g.main);
+              d.main);
+    check_scalars_dev(pool.as<Fr>(), n * stride, 0, 1, flag.as<uint32_t>(), d.main);
     R1csArgs ra;
     ra.nthreads = n * rows;
     for (int k = 0; k < 3; ++k) {
@@ -622,14 +885,14 @@ int mb200_circuit_rows(const mb200_circuit* c, size_t n, const uint8_t* inputs, 
     ra.idx_inputs = c->n_aux;
     ra.abc = abc.as<Fr>();
     ra.order = R.order.as<uint32_t>();
-    launch_r1cs_eval(ra, g.main);
+    launch_r1cs_eval(ra, d.main);
     uint32_t bad = 0;
-    copy_d2h(&bad, flag.p, 4, g.main);
+    copy_d2h(&bad, flag.p, 4, d.main);
     uint8_t* outs[3] = {a_out, b_out, c_out};
     for (size_t i = 0; i < n; ++i)
         for (int k = 0; k < 3; ++k)
-            copy_d2h(outs[k] + i * rows * 32, abc.as<uint8_t>() + (i * 3 + k) * rows * 32, rows * 32, g.main);
-    stream_sync(g.main);
+            copy_d2h(outs[k] + i * rows * 32, abc.as<uint8_t>() + (i * 3 + k) * rows * 32, rows * 32, d.main);
+    stream_sync(d.main);
     if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
     MB_API_END
 }
@@ -637,10 +900,10 @@ int mb200_circuit_rows(const mb200_circuit* c, size_t n, const uint8_t* inputs, 
 int mb200_verify_batch(const mb200_params* p, size_t n, const uint8_t* proofs_uncompressed, const uint8_t* inputs,
                        uint8_t* ok_out) {
     MB_API_BEGIN
-    require_init();
-    if (!p || !p->p || (n && (!proofs_uncompressed || !inputs || !ok_out))) fail(MB200_EINVAL, "null argument%s", "");
+    Device& d = dev0();
+    if (n && (!proofs_uncompressed || !inputs || !ok_out)) fail(MB200_EINVAL, "null argument%s", "");
     if (n == 0) return MB200_OK;
-    const Params& P = *p->p;
+    const Params& P = *replicas(p)[0];
     // A | B | C in zkcrypto uncompressed form -> three device arrays
     std::vector<uint8_t> ha(n * 96), hb(n * 192), hc(n * 96);
     for (size_t i = 0; i < n; ++i) {
@@ -650,17 +913,17 @@ int mb200_verify_batch(const mb200_params* p, size_t n, const uint8_t* proofs_un
     }
     DevBuf ra(n * 96), rb(n * 192), rc(n * 96), pa(n * sizeof(G1Affine)), pb(n * sizeof(G2Affine)),
         pc(n * sizeof(G1Affine)), bad(4), din(n * P.n_inputs * 32), ok(n * 4);
-    copy_h2d(ra.p, ha.data(), ha.size(), g.main);
-    copy_h2d(rb.p, hb.data(), hb.size(), g.main);
-    copy_h2d(rc.p, hc.data(), hc.size(), g.main);
-    copy_h2d(din.p, inputs, n * P.n_inputs * 32, g.main);
-    dev_memset(bad.p, 0, 4, g.main);
-    DecodeArgs d1{n, ra.as<uint8_t>(), pa.p, bad.as<uint32_t>()}, d2{n, rb.as<uint8_t>(), pb.p, bad.as<uint32_t>()},
-        d3{n, rc.as<uint8_t>(), pc.p, bad.as<uint32_t>()};
-    launch_decode_g1(d1, g.main);
-    launch_decode_g2(d2, g.main);
-    launch_decode_g1(d3, g.main);
-    check_scalars_dev(din.as<Fr>(), n * P.n_inputs, 0, 1, bad.as<uint32_t>(), g.main);
+    copy_h2d(ra.p, ha.data(), ha.size(), d.main);
+    copy_h2d(rb.p, hb.data(), hb.size(), d.main);
+    copy_h2d(rc.p, hc.data(), hc.size(), d.main);
+    copy_h2d(din.p, inputs, n * P.n_inputs * 32, d.main);
+    dev_memset(bad.p, 0, 4, d.main);
+    DecodeArgs d1{n, ra.as<uint8_t>(), pa.p, bad.as<uint32_t>(), 1}, d2{n, rb.as<uint8_t>(), pb.p, bad.as<uint32_t>(), 1},
+        d3{n, rc.as<uint8_t>(), pc.p, bad.as<uint32_t>(), 1};
+    launch_decode_g1(d1, d.main);
+    launch_decode_g2(d2, d.main);
+    launch_decode_g1(d3, d.main);
+    check_scalars_dev(din.as<Fr>(), n * P.n_inputs, 0, 1, bad.as<uint32_t>(), d.main);
     VerifyArgs va;
     va.nthreads = n;
     va.pa = pa.as<G1Affine>();
@@ -671,12 +934,12 @@ int mb200_verify_batch(const mb200_params* p, size_t n, const uint8_t* proofs_un
     va.n_inputs = P.n_inputs;
     va.vk = {P.vk_ic.as<G1Affine>(), P.vk_g2.as<G2Affine>() + 1, P.vk_g2.as<G2Affine>() + 2, P.vk_ab.as<Fp12>()};
     va.ok = ok.as<uint32_t>();
-    launch_verify_proofs(va, g.main);
+    launch_verify_proofs(va, d.main);
     std::vector<uint32_t> hok(n);
     uint32_t hbad = 0;
-    copy_d2h(hok.data(), ok.p, n * 4, g.main);
-    copy_d2h(&hbad, bad.p, 4, g.main);
-    stream_sync(g.main);
+    copy_d2h(hok.data(), ok.p, n * 4, d.main);
+    copy_d2h(&hbad, bad.p, 4, d.main);
+    stream_sync(d.main);
     if (hbad) fail(MB200_EPARSE, "malformed point or non-canonical input%s", "");
     for (size_t i = 0; i < n; ++i) ok_out[i] = hok[i] ? 1 : 0;
     MB_API_END
@@ -684,19 +947,19 @@ int mb200_verify_batch(const mb200_params* p, size_t n, const uint8_t* proofs_un
 
 int mb200_verify_proofs(const mb200_params* p, size_t n, const uint8_t* proofs, const uint8_t* inputs, uint8_t* ok_out) {
     MB_API_BEGIN
-    require_init();
-    if (!p || !p->p || (n && (!proofs || !inputs || !ok_out))) fail(MB200_EINVAL, "null argument%s", "");
+    Device& d = dev0();
+    if (n && (!proofs || !inputs || !ok_out)) fail(MB200_EINVAL, "null argument%s", "");
     if (n == 0) return MB200_OK;
-    const Params& P = *p->p;
+    const Params& P = *replicas(p)[0];
     DevBuf raw(n * 192), pa(n * sizeof(G1Affine)), pb(n * sizeof(G2Affine)), pc(n * sizeof(G1Affine)), bad(n * 4),
         flag(4), din(n * P.n_inputs * 32), ok(n * 4);
-    copy_h2d(raw.p, proofs, n * 192, g.main);
-    copy_h2d(din.p, inputs, n * P.n_inputs * 32, g.main);
-    dev_memset(bad.p, 0, n * 4, g.main);
-    dev_memset(flag.p, 0, 4, g.main);
+    copy_h2d(raw.p, proofs, n * 192, d.main);
+    copy_h2d(din.p, inputs, n * P.n_inputs * 32, d.main);
+    dev_memset(bad.p, 0, n * 4, d.main);
+    dev_memset(flag.p, 0, 4, d.main);
     ProofReadArgs ra{n * 3, raw.as<uint8_t>(), pa.as<G1Affine>(), pb.as<G2Affine>(), pc.as<G1Affine>(), bad.as<uint32_t>()};
-    launch_proof_read(ra, g.main);
-    check_scalars_dev(din.as<Fr>(), n * P.n_inputs, 0, 1, flag.as<uint32_t>(), g.main);
+    launch_proof_read(ra, d.main);
+    check_scalars_dev(din.as<Fr>(), n * P.n_inputs, 0, 1, flag.as<uint32_t>(), d.main);
     VerifyArgs va;
     va.nthreads = n;
     va.pa = pa.as<G1Affine>();
@@ -707,13 +970,13 @@ int mb200_verify_proofs(const mb200_params* p, size_t n, const uint8_t* proofs, 
     va.n_inputs = P.n_inputs;
     va.vk = {P.vk_ic.as<G1Affine>(), P.vk_g2.as<G2Affine>() + 1, P.vk_g2.as<G2Affine>() + 2, P.vk_ab.as<Fp12>()};
     va.ok = ok.as<uint32_t>();
-    launch_verify_proofs(va, g.main);
+    launch_verify_proofs(va, d.main);
     std::vector<uint32_t> hok(n), hbad(n);
     uint32_t hflag = 0;
-    copy_d2h(hok.data(), ok.p, n * 4, g.main);
-    copy_d2h(hbad.data(), bad.p, n * 4, g.main);
-    copy_d2h(&hflag, flag.p, 4, g.main);
-    stream_sync(g.main);
+    copy_d2h(hok.data(), ok.p, n * 4, d.main);
+    copy_d2h(hbad.data(), bad.p, n * 4, d.main);
+    copy_d2h(&hflag, flag.p, 4, d.main);
+    stream_sync(d.main);
     if (hflag) fail(MB200_ESCALAR, "a public input is not canonical (>= r)%s", "");
     for (size_t i = 0; i < n; ++i) ok_out[i] = (hok[i] && !hbad[i]) ? 1 : 0;
     MB_API_END
@@ -722,25 +985,30 @@ int mb200_verify_proofs(const mb200_params* p, size_t n, const uint8_t* proofs, 
 int mb200_verify_proofs_batch(const mb200_params* p, size_t n, const uint8_t* proofs, const uint8_t* inputs,
                               const uint8_t* z, int* all_ok) {
     MB_API_BEGIN
-    require_init();
-    if (!p || !p->p || !all_ok || (n && (!proofs || !inputs || !z))) fail(MB200_EINVAL, "null argument%s", "");
+    Device& d = dev0();
+    if (!all_ok || (n && (!proofs || !inputs || !z))) fail(MB200_EINVAL, "null argument%s", "");
     *all_ok = 1;
     if (n == 0) return MB200_OK;
-    const Params& P = *p->p;
+    for (size_t i = 0; i < n; ++i) {  // a zero coefficient would drop proof i from the combined equation
+        bool zero = true;
+        for (int k = 0; k < 16; ++k) zero = zero && z[16 * i + k] == 0;
+        if (zero) fail(MB200_EINVAL, "batch coefficient %s%ld is zero", "", (long)i);
+    }
+    const Params& P = *replicas(p)[0];
     DevBuf raw(n * 192), pa(n * sizeof(G1Affine)), pb(n * sizeof(G2Affine)), pc(n * sizeof(G1Affine)), bad(n * 4),
         flag(4), din(n * P.n_inputs * 32), dz(n * 16), f(n * sizeof(Fp12)), zc(n * sizeof(G1XYZZ)),
         zx(n * P.n_inputs * sizeof(Fr)), ok(4);
-    copy_h2d(raw.p, proofs, n * 192, g.main);
-    copy_h2d(din.p, inputs, n * P.n_inputs * 32, g.main);
-    copy_h2d(dz.p, z, n * 16, g.main);
-    dev_memset(bad.p, 0, n * 4, g.main);
-    dev_memset(flag.p, 0, 4, g.main);
+    copy_h2d(raw.p, proofs, n * 192, d.main);
+    copy_h2d(din.p, inputs, n * P.n_inputs * 32, d.main);
+    copy_h2d(dz.p, z, n * 16, d.main);
+    dev_memset(bad.p, 0, n * 4, d.main);
+    dev_memset(flag.p, 0, 4, d.main);
     ProofReadArgs ra{n * 3, raw.as<uint8_t>(), pa.as<G1Affine>(), pb.as<G2Affine>(), pc.as<G1Affine>(), bad.as<uint32_t>()};
-    launch_proof_read(ra, g.main);
-    check_scalars_dev(din.as<Fr>(), n * P.n_inputs, 0, 1, flag.as<uint32_t>(), g.main);
+    launch_proof_read(ra, d.main);
+    check_scalars_dev(din.as<Fr>(), n * P.n_inputs, 0, 1, flag.as<uint32_t>(), d.main);
     BatchMillerArgs ma{n, pa.as<G1Affine>(), pb.as<G2Affine>(), pc.as<G1Affine>(), din.as<uint32_t>(), P.n_inputs,
                        dz.as<uint32_t>(), f.as<Fp12>(), zc.as<G1XYZZ>(), zx.as<Fr>()};
-    launch_batch_miller(ma, g.main);
+    launch_batch_miller(ma, d.main);
     BatchFinalArgs fa;
     fa.nthreads = 1;
     fa.n = n;
@@ -752,13 +1020,13 @@ int mb200_verify_proofs_batch(const mb200_params* p, size_t n, const uint8_t* pr
     fa.beta = P.vk_g2.as<G2Affine>();
     fa.vk = {P.vk_ic.as<G1Affine>(), P.vk_g2.as<G2Affine>() + 1, P.vk_g2.as<G2Affine>() + 2, P.vk_ab.as<Fp12>()};
     fa.ok = ok.as<uint32_t>();
-    launch_batch_final(fa, g.main);
+    launch_batch_final(fa, d.main);
     std::vector<uint32_t> hbad(n);
     uint32_t hok = 0, hflag = 0;
-    copy_d2h(&hok, ok.p, 4, g.main);
-    copy_d2h(hbad.data(), bad.p, n * 4, g.main);
-    copy_d2h(&hflag, flag.p, 4, g.main);
-    stream_sync(g.main);
+    copy_d2h(&hok, ok.p, 4, d.main);
+    copy_d2h(hbad.data(), bad.p, n * 4, d.main);
+    copy_d2h(&hflag, flag.p, 4, d.main);
+    stream_sync(d.main);
     if (hflag) fail(MB200_ESCALAR, "a public input is not canonical (>= r)%s", "");
     int good = hok ? 1 : 0;
     for (size_t i = 0; i < n; ++i)
@@ -770,9 +1038,10 @@ int mb200_verify_proofs_batch(const mb200_params* p, size_t n, const uint8_t* pr
 int mb200_prove_batch_witness(const mb200_params* p, size_t n_proofs, const uint8_t* inputs, const uint8_t* aux,
                               const uint8_t* r, const uint8_t* s, uint8_t* proofs_out) {
     MB_API_BEGIN
-    if (!p || !p->p) fail(MB200_EINVAL, "null parameters%s", "");
+    require_init();
+    const std::vector<Params*>& reps = replicas(p);
     ProveInputs in{nullptr, nullptr, nullptr, inputs, aux, r, s, false};
-    return prove_impl(*p->p, n_proofs, (size_t)p->p->r1cs.ncons + p->p->n_inputs, in, proofs_out);
+    return prove_impl(reps, n_proofs, (size_t)reps[0]->r1cs.ncons + reps[0]->n_inputs, in, proofs_out);
     MB_API_END
 }
 
@@ -785,59 +1054,59 @@ int mb200_prove_wait(uint64_t ticket) {
 
 int mb200_msm_g1(const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t out[96]) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if ((n && (!bases || !scalars)) || !out) fail(MB200_EINVAL, "null buffer%s", "");
     DevBuf raw(n * 96), pts(n * sizeof(G1Affine)), bad(4), res(sizeof(G1XYZZ)), enc(96);
-    copy_h2d(raw.p, bases, n * 96, g.main);
-    dev_memset(bad.p, 0, 4, g.main);
+    copy_h2d(raw.p, bases, n * 96, d.main);
+    dev_memset(bad.p, 0, 4, d.main);
     DecodeArgs da{n, raw.as<uint8_t>(), pts.p, bad.as<uint32_t>()};
-    launch_decode_g1(da, g.main);
+    launch_decode_g1(da, d.main);
     uint32_t bad_h = 0;
-    copy_d2h(&bad_h, bad.p, 4, g.main);
-    stream_sync(g.main);
+    copy_d2h(&bad_h, bad.p, 4, d.main);
+    stream_sync(d.main);
     if (bad_h) fail(MB200_EPARSE, "malformed G1 encoding%s", "");
-    msm_on_device_bases<Fp>(pts.as<G1Affine>(), scalars, n, res.as<G1XYZZ>());
+    msm_on_device_bases<Fp>(d, pts.as<G1Affine>(), scalars, n, res.as<G1XYZZ>());
     EncodeArgs ea{1, res.p, enc.as<uint8_t>()};
-    launch_encode_g1(ea, g.main);
-    copy_d2h(out, enc.p, 96, g.main);
-    stream_sync(g.main);
+    launch_encode_g1(ea, d.main);
+    copy_d2h(out, enc.p, 96, d.main);
+    stream_sync(d.main);
     MB_API_END
 }
 
 int mb200_msm_g2(const uint8_t* bases, const uint8_t* scalars, size_t n, uint8_t out[192]) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if ((n && (!bases || !scalars)) || !out) fail(MB200_EINVAL, "null buffer%s", "");
     DevBuf raw(n * 192), pts(n * sizeof(G2Affine)), bad(4), res(sizeof(G2XYZZ)), enc(192);
-    copy_h2d(raw.p, bases, n * 192, g.main);
-    dev_memset(bad.p, 0, 4, g.main);
+    copy_h2d(raw.p, bases, n * 192, d.main);
+    dev_memset(bad.p, 0, 4, d.main);
     DecodeArgs da{n, raw.as<uint8_t>(), pts.p, bad.as<uint32_t>()};
-    launch_decode_g2(da, g.main);
+    launch_decode_g2(da, d.main);
     uint32_t bad_h = 0;
-    copy_d2h(&bad_h, bad.p, 4, g.main);
-    stream_sync(g.main);
+    copy_d2h(&bad_h, bad.p, 4, d.main);
+    stream_sync(d.main);
     if (bad_h) fail(MB200_EPARSE, "malformed G2 encoding%s", "");
-    msm_on_device_bases<Fp2>(pts.as<G2Affine>(), scalars, n, res.as<G2XYZZ>());
+    msm_on_device_bases<Fp2>(d, pts.as<G2Affine>(), scalars, n, res.as<G2XYZZ>());
     EncodeArgs ea{1, res.p, enc.as<uint8_t>()};
-    launch_encode_g2(ea, g.main);
-    copy_d2h(out, enc.p, 192, g.main);
-    stream_sync(g.main);
+    launch_encode_g2(ea, d.main);
+    copy_d2h(out, enc.p, 192, d.main);
+    stream_sync(d.main);
     MB_API_END
 }
 
 int mb200_g1_bases_upload(const uint8_t* bases, size_t n, void** dev_bases) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if (!bases || !dev_bases) fail(MB200_EINVAL, "null buffer%s", "");
     DevBuf raw(n * 96), bad(4);
     void* pts = dev_alloc(n * sizeof(G1Affine));
-    copy_h2d(raw.p, bases, n * 96, g.main);
-    dev_memset(bad.p, 0, 4, g.main);
+    copy_h2d(raw.p, bases, n * 96, d.main);
+    dev_memset(bad.p, 0, 4, d.main);
     DecodeArgs da{n, raw.as<uint8_t>(), pts, bad.as<uint32_t>()};
-    launch_decode_g1(da, g.main);
+    launch_decode_g1(da, d.main);
     uint32_t bad_h = 0;
-    copy_d2h(&bad_h, bad.p, 4, g.main);
-    stream_sync(g.main);
+    copy_d2h(&bad_h, bad.p, 4, d.main);
+    stream_sync(d.main);
     if (bad_h) {
         dev_free(pts);
         fail(MB200_EPARSE, "malformed G1 encoding%s", "");
@@ -854,97 +1123,214 @@ int mb200_dev_free(void* p) {
 
 int mb200_msm_g1_partial(const void* dev_bases, const uint8_t* scalars, size_t n, uint8_t out_partial[192]) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if ((n && (!dev_bases || !scalars)) || !out_partial) fail(MB200_EINVAL, "null buffer%s", "");
     DevBuf res(sizeof(G1XYZZ));
-    msm_on_device_bases<Fp>((const G1Affine*)dev_bases, scalars, n, res.as<G1XYZZ>());
-    copy_d2h(out_partial, res.p, sizeof(G1XYZZ), g.main);
-    stream_sync(g.main);
+    msm_on_device_bases<Fp>(d, (const G1Affine*)dev_bases, scalars, n, res.as<G1XYZZ>());
+    copy_d2h(out_partial, res.p, sizeof(G1XYZZ), d.main);
+    stream_sync(d.main);
     MB_API_END
 }
 
 int mb200_g1_sum_partials(const uint8_t* partials, size_t count, uint8_t out[96]) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if ((count && !partials) || !out) fail(MB200_EINVAL, "null buffer%s", "");
     DevBuf parts(count * sizeof(G1XYZZ)), enc(96);
-    copy_h2d(parts.p, partials, count * sizeof(G1XYZZ), g.main);
+    copy_h2d(parts.p, partials, count * sizeof(G1XYZZ), d.main);
     SumPartialsArgs sa{1, parts.as<G1XYZZ>(), count, enc.as<uint8_t>()};
-    launch_sum_partials(sa, g.main);
-    copy_d2h(out, enc.p, 96, g.main);
-    stream_sync(g.main);
+    launch_sum_partials(sa, d.main);
+    copy_d2h(out, enc.p, 96, d.main);
+    stream_sync(d.main);
+    MB_API_END
+}
+
+int mb200_msm_g1_partial_device(const void* dev_bases, const uint8_t* scalars, size_t n, void* dev_partial) {
+    MB_API_BEGIN
+    Device& d = dev0();
+    if ((n && (!dev_bases || !scalars)) || !dev_partial) fail(MB200_EINVAL, "null buffer%s", "");
+    msm_on_device_bases<Fp>(d, (const G1Affine*)dev_bases, scalars, n, (G1XYZZ*)dev_partial);
+    MB_API_END
+}
+
+int mb200_g1_sum_partials_device(const void* dev_partials, size_t count, uint8_t out[96]) {
+    MB_API_BEGIN
+    Device& d = dev0();
+    if ((count && !dev_partials) || !out) fail(MB200_EINVAL, "null buffer%s", "");
+    DevBuf enc(96);
+    SumPartialsArgs sa{1, (const G1XYZZ*)dev_partials, count, enc.as<uint8_t>()};
+    launch_sum_partials(sa, d.main);
+    copy_d2h(out, enc.p, 96, d.main);
+    stream_sync(d.main);
+    MB_API_END
+}
+
+}  // extern "C"
+
+// Bases of a single large MSM, range-split over the opened devices (BASELINE config 3 inside one
+// process): shard k holds bases [lo_k, hi_k) decoded into Montgomery form on device slot k.
+struct mb200_g1_bases {
+    size_t n = 0;
+    std::vector<size_t> lo;      // nd + 1 boundaries
+    std::vector<void*> shard;    // device pointers, one per slot (nullptr for an empty range)
+    std::vector<void*> partial;  // one XYZZ per slot, on that slot's device
+};
+static void g1_bases_destroy(mb200_g1_bases* b) {
+    if (!b) return;
+    for (size_t k = 0; k < b->shard.size() && k < g.devs.size(); ++k) {
+#ifndef MB200_EMU
+        cudaSetDevice(g.devs[k]->id);
+#endif
+        dev_free(b->shard[k]);
+        dev_free(b->partial[k]);
+    }
+#ifndef MB200_EMU
+    if (!g.devs.empty()) cudaSetDevice(g.devs[0]->id);
+#endif
+    delete b;
+}
+
+extern "C" {
+
+int mb200_g1_bases_new(const uint8_t* bases, size_t n, mb200_g1_bases** out) {
+    MB_API_BEGIN
+    require_init();
+    if (!out || (n && !bases)) fail(MB200_EINVAL, "null buffer%s", "");
+    *out = nullptr;
+    const size_t nd = g.devs.size();
+    std::unique_ptr<mb200_g1_bases, void (*)(mb200_g1_bases*)> B(new mb200_g1_bases(), g1_bases_destroy);
+    B->n = n;
+    B->lo.resize(nd + 1);
+    for (size_t k = 0; k <= nd; ++k) B->lo[k] = n / nd * k + std::min(k, n % nd);
+    B->shard.assign(nd, nullptr);
+    B->partial.assign(nd, nullptr);
+    for_devices(all_devices(), [&](Device& d) {
+        const size_t lo = B->lo[d.slot], cnt = B->lo[d.slot + 1] - lo;
+        B->partial[d.slot] = dev_alloc(sizeof(G1XYZZ));
+        if (!cnt) return;
+        DevBuf raw(cnt * 96), bad(4);
+        B->shard[d.slot] = dev_alloc(cnt * sizeof(G1Affine));
+        copy_h2d(raw.p, bases + lo * 96, cnt * 96, d.main);
+        dev_memset(bad.p, 0, 4, d.main);
+        DecodeArgs da{cnt, raw.as<uint8_t>(), B->shard[d.slot], bad.as<uint32_t>()};
+        launch_decode_g1(da, d.main);
+        uint32_t bad_h = 0;
+        copy_d2h(&bad_h, bad.p, 4, d.main);
+        stream_sync(d.main);
+        if (bad_h) fail(MB200_EPARSE, "malformed G1 encoding%s", "");
+    });
+    *out = B.release();
+    MB_API_END
+}
+
+void mb200_g1_bases_free(mb200_g1_bases* b) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    g1_bases_destroy(b);
+}
+
+/* sum_i s_i B_i with the bases split over the devices: every device reduces its range to one
+ * XYZZ partial, the partials travel GPU -> GPU into slot 0's memory (cudaMemcpyPeerAsync: NVLink,
+ * no host hop) and one thread there adds them and encodes the result -- SURVEY.md's K6. */
+int mb200_msm_g1_bases(const mb200_g1_bases* b, const uint8_t* scalars, size_t n, uint8_t out[96]) {
+    MB_API_BEGIN
+    require_init();
+    if (!b || !out || (n && !scalars)) fail(MB200_EINVAL, "null buffer%s", "");
+    if (n != b->n || b->shard.size() != g.devs.size()) fail(MB200_EINVAL, "scalar count does not match the bases%s (%ld)", "", (long)b->n);
+    const size_t nd = g.devs.size();
+    Device& d0 = *g.devs[0];
+    use(d0);
+    d0.peer_parts.ensure(nd * sizeof(G1XYZZ));
+    G1XYZZ* gathered = d0.peer_parts.as<G1XYZZ>();
+    for_devices(all_devices(), [&](Device& d) {
+        const size_t lo = b->lo[d.slot], cnt = b->lo[d.slot + 1] - lo;
+        G1XYZZ* part = (G1XYZZ*)b->partial[d.slot];
+        msm_on_device_bases<Fp>(d, (const G1Affine*)b->shard[d.slot], scalars + lo * 32, cnt, part);
+#ifndef MB200_EMU
+        if (d.slot == 0) MB_CUDA(cudaMemcpyAsync(gathered, part, sizeof(G1XYZZ), cudaMemcpyDeviceToDevice, d.main));
+        else MB_CUDA(cudaMemcpyPeerAsync(gathered + d.slot, d0.id, part, d.id, sizeof(G1XYZZ), d.main));
+        stream_sync(d.main);
+#else
+        memcpy(gathered + d.slot, part, sizeof(G1XYZZ));
+#endif
+    });
+    use(d0);
+    DevBuf enc(96);
+    SumPartialsArgs sa{1, gathered, nd, enc.as<uint8_t>()};
+    launch_sum_partials(sa, d0.main);
+    copy_d2h(out, enc.p, 96, d0.main);
+    stream_sync(d0.main);
     MB_API_END
 }
 
 int mb200_ntt(uint8_t* data, unsigned log_n, int inverse, int coset) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if (!data) fail(MB200_EINVAL, "null buffer%s", "");
-    NttCache& c = ntt_cache(log_n);
+    NttCache& c = ntt_cache(d, log_n);
     size_t n = (size_t)1 << log_n;
-    DevBuf d(n * 32), t0(n * 32), t1(n * 32), o(n * 32), flag(4);
-    copy_h2d(d.p, data, n * 32, g.main);
-    dev_memset(flag.p, 0, 4, g.main);
-    check_scalars_dev(d.as<Fr>(), n, 0, 1, flag.as<uint32_t>(), g.main);
+    DevBuf in(n * 32), t0(n * 32), t1(n * 32), o(n * 32), flag(4);
+    copy_h2d(in.p, data, n * 32, d.main);
+    dev_memset(flag.p, 0, 4, d.main);
+    check_scalars_dev(in.as<Fr>(), n, 0, 1, flag.as<uint32_t>(), d.main);
     NttPlan p;
     p.inverse = inverse != 0;
     if (!inverse && coset) p.in_scale = c.gpow.as<Fr>();
     if (inverse) p.out_scale = coset ? c.dom.cos_inv.as<Fr>() : c.dom.minv_tab.as<Fr>();
-    ntt_run(c.dom, p, 1, d.as<Fr>(), n, o.as<Fr>(), n, t0.as<Fr>(), t1.as<Fr>(), g.main);
+    ntt_run(c.dom, p, 1, in.as<Fr>(), n, o.as<Fr>(), n, t0.as<Fr>(), t1.as<Fr>(), d.main);
     uint32_t bad = 0;
-    copy_d2h(&bad, flag.p, 4, g.main);
-    copy_d2h(data, o.p, n * 32, g.main);
-    stream_sync(g.main);
+    copy_d2h(&bad, flag.p, 4, d.main);
+    copy_d2h(data, o.p, n * 32, d.main);
+    stream_sync(d.main);
     if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
     MB_API_END
 }
 
 int mb200_h_coeffs(const uint8_t* a, const uint8_t* b, const uint8_t* c, size_t rows, uint8_t* out) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if (!a || !b || !c || !out || rows < 2) fail(MB200_EINVAL, "bad argument (rows must be >= 2)%s", "");
     unsigned log_n = 0;
     while (((size_t)1 << log_n) < rows) log_n++;
-    NttCache& cache = ntt_cache(log_n);
+    NttCache& cache = ntt_cache(d, log_n);
     size_t n = (size_t)1 << log_n;
     DevBuf abc(3 * rows * 32), w0(3 * n * 32), w1(3 * n * 32), w2(3 * n * 32), w3(3 * n * 32), h(n * 32), flag(4);
-    copy_h2d(abc.as<uint8_t>(), a, rows * 32, g.main);
-    copy_h2d(abc.as<uint8_t>() + rows * 32, b, rows * 32, g.main);
-    copy_h2d(abc.as<uint8_t>() + 2 * rows * 32, c, rows * 32, g.main);
-    dev_memset(flag.p, 0, 4, g.main);
-    check_scalars_dev(abc.as<Fr>(), 3 * rows, 0, 1, flag.as<uint32_t>(), g.main);
+    copy_h2d(abc.as<uint8_t>(), a, rows * 32, d.main);
+    copy_h2d(abc.as<uint8_t>() + rows * 32, b, rows * 32, d.main);
+    copy_h2d(abc.as<uint8_t>() + 2 * rows * 32, c, rows * 32, d.main);
+    dev_memset(flag.p, 0, 4, d.main);
+    check_scalars_dev(abc.as<Fr>(), 3 * rows, 0, 1, flag.as<uint32_t>(), d.main);
     h_pipeline(cache.dom, 1, (uint32_t)rows, abc.as<Fr>(), rows, h.as<Fr>(), n, w0.as<Fr>(), w1.as<Fr>(), w2.as<Fr>(),
-               w3.as<Fr>(), g.main);
+               w3.as<Fr>(), d.main);
     uint32_t bad = 0;
-    copy_d2h(&bad, flag.p, 4, g.main);
-    copy_d2h(out, h.p, (n - 1) * 32, g.main);
-    stream_sync(g.main);
+    copy_d2h(&bad, flag.p, 4, d.main);
+    copy_d2h(out, h.p, (n - 1) * 32, d.main);
+    stream_sync(d.main);
     if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
     MB_API_END
 }
 
-static void fr_mul_dev(const void* a, const void* b, size_t n, void* out) {
+static void fr_mul_dev(Device& d, const void* a, const void* b, size_t n, void* out) {
     FrMulArgs fa{n, (const Fr*)a, (const Fr*)b, (Fr*)out};
-    launch_fr_mul_kernel(fa, g.main);
+    launch_fr_mul_kernel(fa, d.main);
 }
 int mb200_fr_mul(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if (n && (!a || !b || !out)) fail(MB200_EINVAL, "null buffer%s", "");
     DevBuf da(n * 32), db(n * 32), dc(n * 32);
-    copy_h2d(da.p, a, n * 32, g.main);
-    copy_h2d(db.p, b, n * 32, g.main);
-    fr_mul_dev(da.p, db.p, n, dc.p);
-    copy_d2h(out, dc.p, n * 32, g.main);
-    stream_sync(g.main);
+    copy_h2d(da.p, a, n * 32, d.main);
+    copy_h2d(db.p, b, n * 32, d.main);
+    fr_mul_dev(d, da.p, db.p, n, dc.p);
+    copy_d2h(out, dc.p, n * 32, d.main);
+    stream_sync(d.main);
     MB_API_END
 }
 int mb200_fr_mul_device(const void* a, const void* b, size_t n, void* out) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if (n && (!a || !b || !out)) fail(MB200_EINVAL, "null buffer%s", "");
-    fr_mul_dev(a, b, n, out);
-    stream_sync(g.main);
+    fr_mul_dev(d, a, b, n, out);
+    stream_sync(d.main);
     MB_API_END
 }
 
@@ -957,14 +1343,22 @@ int mb200_set_option(const char* name, long value) {
         g.chunk = (uint32_t)value;
     } else if (!strcmp(name, "streams")) {
         if (value < 1 || value > 8) fail(MB200_EINVAL, "streams out of range%s (%ld)", "", value);
-        set_ctx_count((size_t)value);
+        g.n_streams = (uint32_t)value;
+        for (auto& d : g.devs) {
+            use(*d);
+            set_ctx_count(*d, (size_t)value);
+        }
+        use(*g.devs[0]);
     } else if (!strcmp(name, "verify")) {
+        if (value < 0 || value > 2) fail(MB200_EINVAL, "verify out of range%s (%ld)", "", value);
         g.verify = (int)value;
     } else if (!strcmp(name, "profile")) {
+        std::lock_guard<std::mutex> pl(g_msm_profile.mu);
         g_msm_profile.enabled = value != 0;
         g_msm_profile.acc_ms = 0;
         g_msm_profile.acc_launches = 0;
         g_msm_profile.acc_entries_bound = 0;
+        for (auto& ph : g_msm_profile.phase_ms) ph = 0;
     } else {
         fail(MB200_EINVAL, "unknown option %s", name);
     }
@@ -974,49 +1368,61 @@ int mb200_set_option(const char* name, long value) {
 int mb200_get_counter(const char* name, double* value) {
     MB_API_BEGIN
     if (!name || !value) fail(MB200_EINVAL, "null argument%s", "");
-    if (!strcmp(name, "launches")) *value = (double)g_launches;
+    std::lock_guard<std::mutex> pl(g_msm_profile.mu);
+    if (!strcmp(name, "launches")) *value = (double)g_launches.load();
     else if (!strcmp(name, "acc_launches")) *value = (double)g_msm_profile.acc_launches;
     else if (!strcmp(name, "acc_us")) *value = g_msm_profile.acc_ms * 1000.0;
     else if (!strcmp(name, "acc_bytes")) *value = (double)g_msm_profile.acc_entries_bound;
+    else if (!strcmp(name, "msm_upload_us")) *value = g_msm_profile.phase_ms[0] * 1000.0;
+    else if (!strcmp(name, "msm_sort_us")) *value = g_msm_profile.phase_ms[1] * 1000.0;
+    else if (!strcmp(name, "msm_reduce_us")) *value = g_msm_profile.phase_ms[2] * 1000.0;
     else if (!strcmp(name, "last_batch_us")) *value = g.last_batch_ms * 1000.0;
     else if (!strcmp(name, "verified")) *value = (double)g.verified;
     else if (!strcmp(name, "verify_failed")) *value = (double)g.verify_failed;
+    else if (!strcmp(name, "devices")) *value = (double)g.devs.size();
     else fail(MB200_EINVAL, "unknown counter %s", name);
     MB_API_END
 }
 
+// Every opened device runs the self-test; the result is the total number of mismatches.
 int mb200_selftest(void) {
     std::lock_guard<std::mutex> lk(g.mu);
     try {
         require_init();
-        uint32_t bad = 0;
-        DevBuf d(4);
-        dev_memset(d.p, 0, 4, g.main);
-        SelfTestArgs a;
-        a.nthreads = 4096;
-        a.mismatches = d.as<uint32_t>();
-        a.g1 = g1_generator_host();
-        a.g2 = g2_generator_host();
-        launch_selftest_kernel(a, g.main);
-        // pairing: x-chain final exponentiation against the plain power, Frobenius consistency
-        DevBuf gens(sizeof(G1Affine) + sizeof(G2Affine));
-        G1Affine hg1 = g1_generator_host();
-        G2Affine hg2 = g2_generator_host();
-        copy_h2d(gens.p, &hg1, sizeof hg1, g.main);
-        copy_h2d((char*)gens.p + sizeof(G1Affine), &hg2, sizeof hg2, g.main);
-        PairSelfTestArgs pa{1, gens.as<G1Affine>(), (const G2Affine*)((char*)gens.p + sizeof(G1Affine)), d.as<uint32_t>()};
-        launch_pair_selftest(pa, g.main);
-        copy_d2h(&bad, d.p, 4, g.main);
-        stream_sync(g.main);
-        return (int)bad;
+        std::atomic<unsigned> total{0};
+        for_devices(all_devices(), [&](Device& d) {
+            uint32_t bad = 0;
+            DevBuf dv(4);
+            dev_memset(dv.p, 0, 4, d.main);
+            SelfTestArgs a;
+            a.nthreads = 4096;
+            a.mismatches = dv.as<uint32_t>();
+            a.g1 = g1_generator_host();
+            a.g2 = g2_generator_host();
+            launch_selftest_kernel(a, d.main);
+            // pairing: x-chain final exponentiation against the plain power, Frobenius consistency
+            DevBuf gens(sizeof(G1Affine) + sizeof(G2Affine));
+            G1Affine hg1 = g1_generator_host();
+            G2Affine hg2 = g2_generator_host();
+            copy_h2d(gens.p, &hg1, sizeof hg1, d.main);
+            copy_h2d((char*)gens.p + sizeof(G1Affine), &hg2, sizeof hg2, d.main);
+            PairSelfTestArgs pa{1, gens.as<G1Affine>(), (const G2Affine*)((char*)gens.p + sizeof(G1Affine)), dv.as<uint32_t>()};
+            launch_pair_selftest(pa, d.main);
+            copy_d2h(&bad, dv.p, 4, d.main);
+            stream_sync(d.main);
+            total += bad;
+        });
+        return (int)total.load();
     } catch (const Exc& e) {
         return e.code;
+    } catch (const std::bad_alloc&) {
+        return MB200_ENOMEM;
     }
 }
 
 int mb200_bench_fpmul(double* muls_per_second) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if (!muls_per_second) fail(MB200_EINVAL, "null argument%s", "");
 #ifndef MB200_EMU
     FpMulBenchArgs a;
@@ -1024,13 +1430,13 @@ int mb200_bench_fpmul(double* muls_per_second) {
     a.iters = 512;
     DevBuf sink(a.nthreads * sizeof(Fp));
     a.sink = sink.as<Fp>();
-    launch_fpmul_bench(a, g.main);  // warm-up
+    launch_fpmul_bench(a, d.main);  // warm-up
     cudaEvent_t e0, e1;
     MB_CUDA(cudaEventCreate(&e0));
     MB_CUDA(cudaEventCreate(&e1));
-    MB_CUDA(cudaEventRecord(e0, g.main));
-    launch_fpmul_bench(a, g.main);
-    MB_CUDA(cudaEventRecord(e1, g.main));
+    MB_CUDA(cudaEventRecord(e0, d.main));
+    launch_fpmul_bench(a, d.main);
+    MB_CUDA(cudaEventRecord(e1, d.main));
     MB_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
     MB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
@@ -1045,7 +1451,7 @@ int mb200_bench_fpmul(double* muls_per_second) {
 
 int mb200_bench_latency(int mode, double* ns_per_op) {
     MB_API_BEGIN
-    require_init();
+    Device& d = dev0();
     if (!ns_per_op || mode < 0 || mode > 3) fail(MB200_EINVAL, "bad argument%s", "");
 #ifndef MB200_EMU
     LatencyArgs a;
@@ -1055,13 +1461,13 @@ int mb200_bench_latency(int mode, double* ns_per_op) {
     a.g1 = g1_generator_host();
     DevBuf sink(32 * sizeof(Fp));
     a.sink = sink.as<Fp>();
-    launch_latency_kernel(a, g.main);
+    launch_latency_kernel(a, d.main);
     cudaEvent_t e0, e1;
     MB_CUDA(cudaEventCreate(&e0));
     MB_CUDA(cudaEventCreate(&e1));
-    MB_CUDA(cudaEventRecord(e0, g.main));
-    launch_latency_kernel(a, g.main);
-    MB_CUDA(cudaEventRecord(e1, g.main));
+    MB_CUDA(cudaEventRecord(e0, d.main));
+    launch_latency_kernel(a, d.main);
+    MB_CUDA(cudaEventRecord(e1, d.main));
     MB_CUDA(cudaEventSynchronize(e1));
     float ms = 0;
     MB_CUDA(cudaEventElapsedTime(&ms, e0, e1));

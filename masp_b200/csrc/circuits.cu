@@ -370,8 +370,14 @@ int mb200_circuit_synthesize(const mb200_circuit* c, size_t n, const uint8_t* wi
             status = MB200_ENOMEM;
         }
     };
+    // nothing may unwind across the C boundary: a worker that cannot be spawned (std::system_error)
+    // or a failed vector growth just means fewer workers -- the work queue is shared
     std::vector<std::thread> pool;
-    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    try {
+        pool.reserve((size_t)n_threads);
+        for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    } catch (...) {
+    }
     work();
     for (auto& t : pool) t.join();
     return status.load();

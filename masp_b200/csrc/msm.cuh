@@ -19,8 +19,9 @@
 // key load and resident in HBM) all windows of an instance share ONE bucket
 // set: no per-window reduction and no doublings on the proving path.
 #pragma once
+#include <mutex>
+
 #include "ec.cuh"
-#include "pair.cuh"
 
 namespace mb {
 
@@ -254,7 +255,6 @@ struct AccArgs {
     const uint32_t* order;  // thread -> task
     const uint32_t* ntasks;
     XYZZ<F>* partials;      // per task
-    const Affine<F>* direct;  // after pair rounds: the points themselves, bucket-sorted (else nullptr)
 };
 template <class F>
 MB_HD void acc_body(const AccArgs<F>& a, size_t tid) {
@@ -262,211 +262,28 @@ MB_HD void acc_body(const AccArgs<F>& a, size_t tid) {
     uint32_t t = a.order[tid];
     uint32_t n = a.task_len[t];
     XYZZ<F> acc = XYZZ<F>::inf();
-    if (a.direct) {
-        const Affine<F>* q = a.direct + a.task_start[t];
-        MB_NOUNROLL
-        for (uint32_t i = 0; i < n; ++i) xyzz_madd(acc, q[i], false);
-    } else {
-        const uint32_t* e = a.entries + a.task_start[t];
-        MB_NOUNROLL
-        for (uint32_t i = 0; i < n; ++i) {
-            uint32_t ent = e[i];
-            Affine<F> q = a.table[ent >> 1];
-            xyzz_madd(acc, q, (ent & 1) != 0);
-        }
+    const uint32_t* e = a.entries + a.task_start[t];
+    MB_NOUNROLL
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t ent = e[i];
+        Affine<F> q = a.table[ent >> 1];
+        xyzz_madd(acc, q, (ent & 1) != 0);
     }
     a.partials[t] = acc;
 }
 MB_HD void acc_g1_body(const AccArgs<Fp>& a, size_t tid) { acc_body<Fp>(a, tid); }
 MB_HD void acc_g2_body(const AccArgs<Fp2>& a, size_t tid) { acc_body<Fp2>(a, tid); }
 MB_K_MSM_G1(msm_accumulate_g1, AccArgs<Fp>, acc_g1_body, 128)
-// (capped at 128 registers for a fourth resident block it spills ~470 bytes and is 1 % slower:
-// profiles/r01_acc_128reg_ab.jsonl)
+// Measured on B200 and rejected (profiles/r02_variants_ab.jsonl, r01_acc_128reg_ab.jsonl; baseline 492-494
+// Spend proofs/s): a 128-register cap for a fourth resident block (-1 %); the accumulator in shared
+// memory, 4 blocks per SM at 128 registers (414: `no_instructions` stalls x 3.6, the i-cache thrashes with
+// 16 warps at 16 places of a 72 KB loop body); one lock-step block per SM with a barrier per
+// iteration (480: `no_instructions` gone, 94 k -> 1 k samples, but the multiplier drops from 82 % to
+// 78 % busy waiting at the barrier); lock-step with L2 prefetch (476) and with shared accumulators
+// (449).  The plain kernel at 166 registers and 12 warps per SM stays.
 MB_K_MSM_G2(msm_accumulate_g2, AccArgs<Fp2>, acc_g2_body, 64)
-
-// Lock-step variant (opt-in, MB200_ACC_LOCKSTEP=1: G1, =2: G1 and G2, =3: G1 with an L2 prefetch of the
-// next table point, =4: G1 with 512 threads and the accumulators in shared memory; not yet measured on a B200).
-// Why: in the profile of msm_accumulate_g1 the second-largest stall after the IMAD dependency `wait`
-// is `no_instructions` (16 % of the samples): the loop body is ~72 KB of straight-line code and the
-// 12 resident warps of an SM sit at 12 different places in it, so every warp streams the whole body
-// through the instruction caches on its own.  Here ONE block fills the SM (384 threads at 166
-// registers; 256 at 255 for G2) and a barrier closes every iteration, so the three (two) warps of a
-// scheduler fetch the same lines at the same time.  The barrier doubles as the loop condition
-// (`__syncthreads_or`): tasks are handed out longest first, so the trip counts inside a block differ
-// by a few iterations at most.  Results are identical: same additions in the same order per task.
-#if !defined(MB200_EMU) && (defined(MB_DEFINE_MSM_G1) || defined(MB_DEFINE_MSM_G2))
-template <class F, int BLOCK, bool PREFETCH>
-__device__ __forceinline__ void acc_lockstep_body(const AccArgs<F>& a) {
-    const size_t tid = (size_t)blockIdx.x * BLOCK + threadIdx.x;
-    const bool live = tid < *a.ntasks;
-    const uint32_t t = live ? a.order[tid] : 0;
-    const uint32_t n = live ? a.task_len[t] : 0;
-    const uint32_t* e = a.entries + (live ? a.task_start[t] : 0);
-    XYZZ<F> acc = XYZZ<F>::inf();
-    uint32_t nxt = n ? e[0] : 0;
-    MB_NOUNROLL
-    for (uint32_t i = 0; __syncthreads_or(i < n); ++i) {
-        if (i < n) {
-            uint32_t ent = nxt;
-            if (i + 1 < n) {
-                nxt = e[i + 1];
-                if (PREFETCH) {  // level 3: pull the next table point towards L2 while this addition runs
-                    const char* nq = reinterpret_cast<const char*>(a.table + (nxt >> 1));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nq));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nq + sizeof(Affine<F>) - 1));
-                }
-            }
-            Affine<F> q = a.table[ent >> 1];
-            xyzz_madd(acc, q, (ent & 1) != 0);
-        }
-    }
-    if (live) a.partials[t] = acc;
-}
-#endif
-#if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G1)
-__global__ void __launch_bounds__(384, 1) msm_accumulate_g1_lockstep(const AccArgs<Fp> a) {
-    acc_lockstep_body<Fp, 384, false>(a);
-}
-__global__ void __launch_bounds__(384, 1) msm_accumulate_g1_lockstep_pf(const AccArgs<Fp> a) {
-    acc_lockstep_body<Fp, 384, true>(a);
-}
-void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s, bool prefetch) {
-    if (!a.nthreads) return;
-    const unsigned grid = (unsigned)((a.nthreads + 383) / 384);
-    if (prefetch) msm_accumulate_g1_lockstep_pf<<<grid, 384, 0, s>>>(a);
-    else msm_accumulate_g1_lockstep<<<grid, 384, 0, s>>>(a);
-    MB_CUDA(cudaGetLastError());
-    ::mb::g_launches++;
-}
-#else
-void launch_msm_accumulate_g1_lockstep(const AccArgs<Fp>& a, cudaStream_t s, bool prefetch);
-#endif
-// G1 with the accumulator in shared memory (opt-in, MB200_ACC_G1_SMEM=1; not yet measured on a B200): the
-// same idea as for G2 below, here to fit FOUR 128-thread blocks per SM (<= 128 registers) without the spills
-// the register-capped build of the plain kernel had (profiles/r01_acc_128reg_ab.jsonl).
-#if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G1)
-static const int ACC_G1_SMEM_BLOCK = 128, ACC_G1_SMEM_STRIDE = 49;
-__global__ void __launch_bounds__(ACC_G1_SMEM_BLOCK, 4) msm_accumulate_g1_smem(const AccArgs<Fp> a) {
-    __shared__ uint32_t acc_g1_sm[ACC_G1_SMEM_BLOCK * ACC_G1_SMEM_STRIDE];
-    const size_t tid = (size_t)blockIdx.x * ACC_G1_SMEM_BLOCK + threadIdx.x;
-    if (tid >= *a.ntasks) return;
-    XYZZ<Fp>& acc = *reinterpret_cast<XYZZ<Fp>*>(acc_g1_sm + ACC_G1_SMEM_STRIDE * threadIdx.x);
-    const uint32_t t = a.order[tid];
-    const uint32_t n = a.task_len[t];
-    const uint32_t* e = a.entries + a.task_start[t];
-    acc = XYZZ<Fp>::inf();
-    MB_NOUNROLL
-    for (uint32_t i = 0; i < n; ++i) {
-        uint32_t ent = e[i];
-        Affine<Fp> q = a.table[ent >> 1];
-        xyzz_madd(acc, q, (ent & 1) != 0);
-    }
-    a.partials[t] = acc;
-}
-void launch_msm_accumulate_g1_smem(const AccArgs<Fp>& a, cudaStream_t s) {
-    if (!a.nthreads) return;
-    msm_accumulate_g1_smem<<<(unsigned)((a.nthreads + ACC_G1_SMEM_BLOCK - 1) / ACC_G1_SMEM_BLOCK), ACC_G1_SMEM_BLOCK, 0,
-                             s>>>(a);
-    MB_CUDA(cudaGetLastError());
-    ::mb::g_launches++;
-}
-#else
-void launch_msm_accumulate_g1_smem(const AccArgs<Fp>& a, cudaStream_t s);
-#endif
-
-// Both at once (opt-in, MB200_ACC_LOCKSTEP=4): one 512-thread block per SM (16 warps at <= 128 registers),
-// accumulators in shared memory, a barrier per iteration.
-#if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G1)
-static const int ACC_G1_LS4_BLOCK = 512;
-__global__ void __launch_bounds__(ACC_G1_LS4_BLOCK, 1) msm_accumulate_g1_lockstep_smem(const AccArgs<Fp> a) {
-    extern __shared__ uint32_t acc_g1_ls_sm[];
-    const size_t tid = (size_t)blockIdx.x * ACC_G1_LS4_BLOCK + threadIdx.x;
-    const bool live = tid < *a.ntasks;
-    const uint32_t t = live ? a.order[tid] : 0;
-    const uint32_t n = live ? a.task_len[t] : 0;
-    const uint32_t* e = a.entries + (live ? a.task_start[t] : 0);
-    XYZZ<Fp>& acc = *reinterpret_cast<XYZZ<Fp>*>(acc_g1_ls_sm + ACC_G1_SMEM_STRIDE * threadIdx.x);
-    acc = XYZZ<Fp>::inf();
-    MB_NOUNROLL
-    for (uint32_t i = 0; __syncthreads_or(i < n); ++i) {
-        if (i < n) {
-            uint32_t ent = e[i];
-            Affine<Fp> q = a.table[ent >> 1];
-            xyzz_madd(acc, q, (ent & 1) != 0);
-        }
-    }
-    if (live) a.partials[t] = acc;
-}
-void launch_msm_accumulate_g1_lockstep_smem(const AccArgs<Fp>& a, cudaStream_t s) {
-    if (!a.nthreads) return;
-    const int bytes = ACC_G1_LS4_BLOCK * ACC_G1_SMEM_STRIDE * 4;
-    static const bool attr = [] {
-        MB_CUDA(cudaFuncSetAttribute(msm_accumulate_g1_lockstep_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     ACC_G1_LS4_BLOCK * ACC_G1_SMEM_STRIDE * 4));
-        return true;
-    }();
-    (void)attr;
-    msm_accumulate_g1_lockstep_smem<<<(unsigned)((a.nthreads + ACC_G1_LS4_BLOCK - 1) / ACC_G1_LS4_BLOCK),
-                                      ACC_G1_LS4_BLOCK, bytes, s>>>(a);
-    MB_CUDA(cudaGetLastError());
-    ::mb::g_launches++;
-}
-#else
-void launch_msm_accumulate_g1_lockstep_smem(const AccArgs<Fp>& a, cudaStream_t s);
-#endif
-
-// G2 with the accumulator in SHARED memory (opt-in, MB200_ACC_G2_SMEM=1; not yet measured on a B200).
-// msm_accumulate_g2 is the one register-starved kernel of the path: 255 registers, 1.2 KB of spill code,
-// 8 warps per SM.  Its XYZZ<Fp2> accumulator alone is 96 words that live across the whole loop; parked
-// in shared memory (97-word stride per thread: conflict-free word accesses) it costs ~200 LDS / STS per
-// ~9 000-IMAD addition and frees the registers for the multiplier.
-#if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G2)
-static const int ACC_G2_SMEM_BLOCK = 128, ACC_G2_SMEM_STRIDE = 97;
-__global__ void __launch_bounds__(ACC_G2_SMEM_BLOCK, 3) msm_accumulate_g2_smem(const AccArgs<Fp2> a) {
-    extern __shared__ uint32_t acc_g2_sm[];
-    const size_t tid = (size_t)blockIdx.x * ACC_G2_SMEM_BLOCK + threadIdx.x;
-    if (tid >= *a.ntasks) return;
-    XYZZ<Fp2>& acc = *reinterpret_cast<XYZZ<Fp2>*>(acc_g2_sm + ACC_G2_SMEM_STRIDE * threadIdx.x);
-    const uint32_t t = a.order[tid];
-    const uint32_t n = a.task_len[t];
-    const uint32_t* e = a.entries + a.task_start[t];
-    acc = XYZZ<Fp2>::inf();
-    MB_NOUNROLL
-    for (uint32_t i = 0; i < n; ++i) {
-        uint32_t ent = e[i];
-        Affine<Fp2> q = a.table[ent >> 1];
-        xyzz_madd(acc, q, (ent & 1) != 0);
-    }
-    a.partials[t] = acc;
-}
-void launch_msm_accumulate_g2_smem(const AccArgs<Fp2>& a, cudaStream_t s) {
-    if (!a.nthreads) return;
-    const int bytes = ACC_G2_SMEM_BLOCK * ACC_G2_SMEM_STRIDE * 4;
-    static const bool attr = [] {
-        MB_CUDA(cudaFuncSetAttribute(msm_accumulate_g2_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     ACC_G2_SMEM_BLOCK * ACC_G2_SMEM_STRIDE * 4));
-        return true;
-    }();
-    (void)attr;
-    msm_accumulate_g2_smem<<<(unsigned)((a.nthreads + ACC_G2_SMEM_BLOCK - 1) / ACC_G2_SMEM_BLOCK), ACC_G2_SMEM_BLOCK,
-                             bytes, s>>>(a);
-    MB_CUDA(cudaGetLastError());
-    ::mb::g_launches++;
-}
-#else
-void launch_msm_accumulate_g2_smem(const AccArgs<Fp2>& a, cudaStream_t s);
-#endif
-#if !defined(MB200_EMU) && defined(MB_DEFINE_MSM_G2)
-__global__ void __launch_bounds__(256, 1) msm_accumulate_g2_lockstep(const AccArgs<Fp2> a) { acc_lockstep_body<Fp2, 256, false>(a); }
-void launch_msm_accumulate_g2_lockstep(const AccArgs<Fp2>& a, cudaStream_t s) {
-    if (!a.nthreads) return;
-    msm_accumulate_g2_lockstep<<<(unsigned)((a.nthreads + 255) / 256), 256, 0, s>>>(a);
-    MB_CUDA(cudaGetLastError());
-    ::mb::g_launches++;
-}
-#else
-void launch_msm_accumulate_g2_lockstep(const AccArgs<Fp2>& a, cudaStream_t s);
-#endif
+// (its accumulator in shared memory -- 168 registers, 12 warps per SM instead of 255 and 8 --
+// measured 457 against 492 proofs/s: the ~800 LDS / STS per addition cost more than the spills.)
 
 // bucket sum = sum of its segments' partial sums (one for almost every bucket)
 template <class F>
@@ -585,63 +402,28 @@ MB_K_RED_G2(msm_horner_g2, HornerArgs<Fp2>, horner_g2_body, 32)
 struct MsmScratch {
     DevBuf counts, offsets, cursor, partial, entries, buckets, lx[2], lp[2], order, ohist;
     DevBuf nseg, seg_off, task_bucket, task_start, task_len, ntasks, partials;
-    DevBuf pw[2], poff[2], pcnt[2];  // pair rounds: ping-pong point buffers and per-bucket layouts
-    DevBuf ppre, pprod, pinv, plast, pscr;  // pair rounds: prefixes, thread products, their inverses, scratch
 };
 
-struct MsmProfile {  // optional CUDA-event timing of the accumulate kernel
+struct MsmProfile {  // optional CUDA-event timing of the accumulate kernel (all devices add into it)
+    std::mutex mu;
     bool enabled = false;
     double acc_ms = 0;
     unsigned long long acc_launches = 0;
     unsigned long long acc_entries_bound = 0;
+    double phase_ms[3] = {0, 0, 0};  // standalone MSM: scalar upload, digit sort, bucket reduction
 };
 extern MsmProfile g_msm_profile;
 
-static const uint32_t RED_T = 16, RED_LOG_T = 4, SCAN_CHUNK = 512;
-inline uint32_t red_log_t(const char* name, uint32_t dflt) {
-    const char* v = getenv(name);
-    uint32_t x = (v && *v) ? (uint32_t)strtoul(v, nullptr, 10) : dflt;
-    return x < 1 ? 1 : (x > 8 ? 8 : x);
-}
+static const uint32_t SCAN_CHUNK = 512;
+// reduction fan-in (log2): wide at level 0, narrow above it -- swept on B200 (profiles/r01_reduce_fanin_sweep.jsonl)
+static const uint32_t RED_LOG_T0 = 3, RED_LOG_T1 = 2;
 
 template <class F>
 inline void launch_acc(const AccArgs<F>& a, cudaStream_t s);
-inline uint32_t msm_acc_lockstep() {
-#ifdef MB200_EMU
-    return 0;  // a barrier has no host counterpart; the variant adds no arithmetic of its own
-#else
-    static const uint32_t v = [] {
-        const char* e = getenv("MB200_ACC_LOCKSTEP");
-        return (e && *e) ? (uint32_t)strtoul(e, nullptr, 10) : 0u;
-    }();
-    return v;
-#endif
-}
 template <>
-inline void launch_acc<Fp>(const AccArgs<Fp>& a, cudaStream_t s) {
-#ifndef MB200_EMU
-    if (msm_acc_lockstep() == 4 && !a.direct) return launch_msm_accumulate_g1_lockstep_smem(a, s);
-    if (msm_acc_lockstep() >= 1 && !a.direct) return launch_msm_accumulate_g1_lockstep(a, s, msm_acc_lockstep() == 3);
-    static const bool g1_smem = [] {
-        const char* e = getenv("MB200_ACC_G1_SMEM");
-        return e && *e && *e != '0';
-    }();
-    if (g1_smem && !a.direct) return launch_msm_accumulate_g1_smem(a, s);
-#endif
-    launch_msm_accumulate_g1(a, s);
-}
+inline void launch_acc<Fp>(const AccArgs<Fp>& a, cudaStream_t s) { launch_msm_accumulate_g1(a, s); }
 template <>
-inline void launch_acc<Fp2>(const AccArgs<Fp2>& a, cudaStream_t s) {
-#ifndef MB200_EMU
-    if (msm_acc_lockstep() == 2 && !a.direct) return launch_msm_accumulate_g2_lockstep(a, s);
-    static const bool g2_smem = [] {
-        const char* e = getenv("MB200_ACC_G2_SMEM");
-        return e && *e && *e != '0';
-    }();
-    if (g2_smem && !a.direct) return launch_msm_accumulate_g2_smem(a, s);
-#endif
-    launch_msm_accumulate_g2(a, s);
-}
+inline void launch_acc<Fp2>(const AccArgs<Fp2>& a, cudaStream_t s) { launch_msm_accumulate_g2(a, s); }
 template <class F>
 inline void launch_combine(const CombineArgs<F>& a, cudaStream_t s);
 template <>
@@ -661,69 +443,13 @@ inline void launch_horner<Fp>(const HornerArgs<Fp>& a, cudaStream_t s) { launch_
 template <>
 inline void launch_horner<Fp2>(const HornerArgs<Fp2>& a, cudaStream_t s) { launch_msm_horner_g2(a, s); }
 
-// Optional second stream for the latency-bound part of an MSM (bucket combine + reduction):
-// `ev` is recorded on the main stream after the accumulation and awaited by `stream`.
-struct MsmTail {
-    cudaStream_t stream = 0;
-#ifndef MB200_EMU
-    cudaEvent_t ev = nullptr;
-#endif
-    bool on() const {
-#ifndef MB200_EMU
-        return ev != nullptr;
-#else
-        return false;
-#endif
-    }
-};
-
-// Runs one class over n_inst instances.  out: n_inst XYZZ results (device), complete on
-// tail.stream if a tail is given, else on s.
-inline uint32_t msm_env(const char* name, uint32_t dflt) {
-    const char* v = getenv(name);
-    return (v && *v) ? (uint32_t)strtoul(v, nullptr, 10) : dflt;
-}
-// pair rounds in front of the accumulation (pair.cuh) and the instances per pass: the
-// intermediate points of a pass must fit the ping-pong buffers, so a batch is cut into passes
-// Default 0: measured on B200 the rounds cost more than they save (profiles/r01_pair_rounds_v2_sweep.jsonl:
-// 484 proofs/s without, 434 / 416 / 402 with 1 / 2 / 3 rounds) -- the two gathers per addition and the
-// prefix traffic make pair_b run at 0.8x of an XYZZ addition instead of the 0.5x its multiplications
-// suggest.  Kept as an opt-in experiment (MB200_PAIR_ROUNDS=n), covered by tests/test_emu.py.
-inline uint32_t msm_pair_rounds() {
-    static const uint32_t r = msm_env("MB200_PAIR_ROUNDS", 0);
-    return r > 8 ? 8 : r;
-}
-inline uint32_t msm_pair_b() {
-    static const uint32_t b = msm_env("MB200_PAIR_B", 32);
-    return b < 1 ? 1 : (b > 1024 ? 1024 : b);
-}
-inline uint32_t msm_pass_instances() {
-    static const uint32_t n = msm_env("MB200_PASS_INSTANCES", 16);
-    return n < 1 ? 1 : n;
-}
-
-template <class F>
-void msm_run_core(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t pool_stride, XYZZ<F>* out,
-                  MsmScratch& w, cudaStream_t s, const MsmTail& tail, uint32_t rounds);
-
+// Runs one class over n_inst instances.  out: n_inst XYZZ results (device), complete on s.
+// (Batched-affine "pair rounds" in front of the accumulation -- 6 instead of 10 multiplications per
+// addition, one shared inversion per launch -- were built and measured in round 1: 434 / 416 / 402
+// proofs/s with 1 / 2 / 3 rounds against 484 without, profiles/r01_pair_rounds_v2_sweep.jsonl; removed.)
 template <class F>
 void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t pool_stride, XYZZ<F>* out,
-             MsmScratch& w, cudaStream_t s, const MsmTail& tail = MsmTail()) {
-    const uint32_t rounds = msm_pair_rounds();
-    if (rounds == 0) {
-        msm_run_core<F>(k, n_inst, pool, pool_stride, out, w, s, tail, 0);
-        return;
-    }
-    const uint32_t pass = msm_pass_instances();
-    for (uint32_t i0 = 0; i0 < n_inst; i0 += pass) {
-        uint32_t n = n_inst - i0 < pass ? n_inst - i0 : pass;
-        msm_run_core<F>(k, n, pool + (size_t)i0 * pool_stride * 8, pool_stride, out + i0, w, s, MsmTail(), rounds);
-    }
-}
-
-template <class F>
-void msm_run_core(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t pool_stride, XYZZ<F>* out,
-                  MsmScratch& w, cudaStream_t s, const MsmTail& tail, uint32_t rounds) {
+             MsmScratch& w, cudaStream_t s) {
     if (n_inst == 0) return;
     size_t nbuckets = (size_t)n_inst * k.inst_stride;
     size_t max_entries = (size_t)n_inst * k.n_bases * k.nwin;
@@ -764,51 +490,8 @@ void msm_run_core(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size
 
     launch_msm_scatter(da, s);
 
-    // pair rounds: halve every bucket `rounds` times with shared-inversion affine additions
     const uint32_t* b_counts = w.counts.as<uint32_t>();
     const uint32_t* b_offsets = w.offsets.as<uint32_t>();
-    const Affine<F>* direct = nullptr;
-    {
-        size_t slots = max_entries;  // bound on the index space of the round's input
-        for (uint32_t r = 0; r < rounds; ++r) {
-            slots = (slots + nbuckets + 1) / 2 + 1;
-            DevBuf& wout = w.pw[r & 1];
-            wout.ensure(slots * sizeof(Affine<F>));
-            w.poff[r & 1].ensure((nbuckets + 1) * 4);
-            w.pcnt[r & 1].ensure(nbuckets * 4);
-            PairArgs<F> pa;
-            pa.nbuckets = (uint32_t)nbuckets;
-            pa.off_in = b_offsets;
-            pa.cnt_in = b_counts;
-            pa.off_out = w.poff[r & 1].as<uint32_t>();
-            pa.cnt_out = w.pcnt[r & 1].as<uint32_t>();
-            pa.table = (const Affine<F>*)k.table;
-            pa.entries = r == 0 ? w.entries.as<uint32_t>() : nullptr;
-            pa.win = direct;
-            pa.wout = wout.as<Affine<F>>();
-            pa.nthreads = nbuckets + 1;
-            PairLaunch<F>::layout(pa, s);
-            const uint32_t B = msm_pair_b();
-            const size_t T = (slots + B - 1) / B;
-            w.ppre.ensure((size_t)B * T * sizeof(F));
-            w.pprod.ensure(T * sizeof(F));
-            w.pinv.ensure(T * sizeof(F));
-            w.plast.ensure(T * 4);
-            w.pscr.ensure(binv_scratch_elems(T) * sizeof(F));
-            pa.B = B;
-            pa.nthreads = T;
-            pa.gpre = w.ppre.as<F>();
-            pa.gprod = w.pprod.as<F>();
-            pa.ginv = w.pinv.as<F>();
-            pa.glast = w.plast.as<uint32_t>();
-            PairLaunch<F>::pa(pa, s);
-            batch_inverse_device<F>(w.pprod.as<F>(), T, w.pinv.as<F>(), w.pscr.as<F>(), s);
-            PairLaunch<F>::pb(pa, s);
-            b_offsets = pa.off_out;
-            b_counts = pa.cnt_out;
-            direct = pa.wout;
-        }
-    }
 
     // tasks: segments of at most SEG_LEN entries, longest first
     size_t max_tasks = nbuckets + max_entries / SEG_LEN + 1;
@@ -870,7 +553,6 @@ void msm_run_core(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size
     aa.order = w.order.as<uint32_t>();
     aa.ntasks = w.ntasks.as<uint32_t>();
     aa.partials = w.partials.as<XYZZ<F>>();
-    aa.direct = direct;
 #ifndef MB200_EMU
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_msm_profile.enabled) {
@@ -886,18 +568,14 @@ void msm_run_core(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size
         MB_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
         MB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-        g_msm_profile.acc_ms += ms;
-        g_msm_profile.acc_launches++;
-        g_msm_profile.acc_entries_bound += (unsigned long long)n_inst * k.n_bases * (sizeof(Affine<F>) + 32);
+        {
+            std::lock_guard<std::mutex> pl(g_msm_profile.mu);
+            g_msm_profile.acc_ms += ms;
+            g_msm_profile.acc_launches++;
+            g_msm_profile.acc_entries_bound += (unsigned long long)n_inst * k.n_bases * (sizeof(Affine<F>) + 32);
+        }
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
-    }
-#endif
-#ifndef MB200_EMU
-    if (tail.on()) {
-        MB_CUDA(cudaEventRecord(tail.ev, s));
-        MB_CUDA(cudaStreamWaitEvent(tail.stream, tail.ev, 0));
-        s = tail.stream;
     }
 #endif
     CombineArgs<F> ca;
@@ -917,9 +595,8 @@ void msm_run_core(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size
     uint32_t level = 0, shift = 0;
     // fan-in: wide at level 0 (many chunks: throughput-bound), narrow above it (few threads:
     // the serial chain of 2 T additions per level is what the stream waits for)
-    static const uint32_t log_t0 = red_log_t("MB200_RED_LOG_T0", 3), log_t1 = red_log_t("MB200_RED_LOG_T1", 2);
     for (;;) {
-        const uint32_t log_t = level == 0 ? log_t0 : log_t1, T = 1u << log_t;
+        const uint32_t log_t = level == 0 ? RED_LOG_T0 : RED_LOG_T1, T = 1u << log_t;
         RedArgs<F> ra;
         ra.X = X;
         ra.P = P;

@@ -6,15 +6,19 @@
 // domain is bellman's: omega = ROOT_OF_UNITY^(2^(32 - log m)),
 // ROOT_OF_UNITY = 7^((r-1)/2^32), coset generator 7.
 //
-// Formulation: out-of-place Stockham autosort passes of radix 8 (tail pass of
-// radix 4 or 2), one thread per radix-point butterfly held in registers,
-// natural order in and out, no bit-reversal pass.  Data stay in PLAIN form
+// Formulation: Stockham autosort, natural order in and out, no bit-reversal pass.  For the
+// sizes the circuits use (2^12 ... 2^18) a transform is TWO shared-memory kernels
+// (ntt_smem.cuh: 2 + 2 sweeps over HBM, the first kernel's contiguous runs stored with TMA bulk
+// copies); other sizes run one radix-8 pass per launch (tail pass of radix 4 or 2), one thread
+// per radix-point butterfly held in registers.  Measured on B200 (profiles/r02_variants_ab.jsonl):
+// 492 -> 517 Spend proofs/s for the shared-memory form, 522 with the six-transform H pipeline
+// below.  Data stay in PLAIN form
 // end to end: with the twiddles stored in Montgomery form, montmul(x, w*R)
 // = x*w, so no conversion pass is needed on either side.  The scalings are
 // fused into the first / last pass of a transform:
 //   ifft  1/m and coset g^i      -> in_scale of the following coset fft
-//   a*b-c and 1/Z(g)             -> "pointwise" load of the final inverse
-//   1/m and g^-i                 -> out_scale of the final inverse
+//   a*b                          -> "pointwise" load of the final inverse
+//   1/m and g^-i, - c(X), 1/Z(g) -> out_scale / sub / post_k of the final inverse's last store
 #pragma once
 #include "field.cuh"
 
@@ -33,18 +37,15 @@ struct NttArgs {
     const Fr* tw;         // omega^i, Montgomery form, n entries
     const Fr* in_scale;   // optional, Montgomery form, indexed by source position
     const Fr* out_scale;  // optional, Montgomery form, indexed by destination position
-    // pointwise load: x = montmul(montmul(a, b), k1) - montmul(c, k2); b, c as src
+    // pointwise load: x = a * b (plain product); b laid out as src
     const Fr* srcb;
-    const Fr* srcc;
-    Fr k1, k2;
-    // EXT kernels only (six-transform H pipeline): srcb without srcc = plain product on load;
     // sub: after out_scale, val = (val - sub[o] * k3) * k2 on the last store
     const Fr* sub;
     size_t sub_stride;
-    Fr k3;
+    Fr k2, k3;
 };
 
-template <int K, bool EXT = false>
+template <int K>
 MB_HD void ntt_body(const NttArgs& a, size_t tid) {
     constexpr int R = 1 << K;
     const uint32_t n = 1u << a.log_n;
@@ -59,15 +60,7 @@ MB_HD void ntt_body(const NttArgs& a, size_t tid) {
         uint32_t idx = j + (uint32_t)r * per;
         if (idx < a.src_len) {
             v[r] = src[idx];
-            if (a.srcb) {
-                Fr b = a.srcb[item * a.src_stride + idx];
-                if (EXT && !a.srcc) {
-                    v[r] = Fr::mul(Fr::mul(v[r], b), Fr::r2());
-                } else {
-                    Fr c = a.srcc[item * a.src_stride + idx];
-                    v[r] = Fr::sub(Fr::mul(Fr::mul(v[r], b), a.k1), Fr::mul(c, a.k2));
-                }
-            }
+            if (a.srcb) v[r] = Fr::mul(Fr::mul(v[r], a.srcb[item * a.src_stride + idx]), Fr::r2());
             if (a.in_scale) v[r] = Fr::mul(v[r], a.in_scale[idx]);
         } else {
             v[r] = Fr::zero();
@@ -114,28 +107,19 @@ MB_HD void ntt_body(const NttArgs& a, size_t tid) {
         uint32_t o = j0 + (uint32_t)q * a.ns;
         Fr val = v[i];
         if (a.out_scale) val = Fr::mul(val, a.out_scale[o]);
-        if (EXT && a.sub) val = Fr::mul(Fr::sub(val, Fr::mul(a.sub[item * a.sub_stride + o], a.k3)), a.k2);
+        if (a.sub) val = Fr::mul(Fr::sub(val, Fr::mul(a.sub[item * a.sub_stride + o], a.k3)), a.k2);
         dst[o] = val;
     }
 }
-MB_HD void ntt1x_body(const NttArgs& a, size_t tid) { ntt_body<1, true>(a, tid); }
-MB_HD void ntt2x_body(const NttArgs& a, size_t tid) { ntt_body<2, true>(a, tid); }
-MB_HD void ntt3x_body(const NttArgs& a, size_t tid) { ntt_body<3, true>(a, tid); }
-MB_K_NTT(ntt_pass_r2_ext, NttArgs, ntt1x_body, 128)
-MB_K_NTT(ntt_pass_r4_ext, NttArgs, ntt2x_body, 128)
-MB_K_NTT(ntt_pass_r8_ext, NttArgs, ntt3x_body, 128)
 MB_HD void ntt1_body(const NttArgs& a, size_t tid) { ntt_body<1>(a, tid); }
 MB_HD void ntt2_body(const NttArgs& a, size_t tid) { ntt_body<2>(a, tid); }
 MB_HD void ntt3_body(const NttArgs& a, size_t tid) { ntt_body<3>(a, tid); }
 MB_K_NTT(ntt_pass_r2, NttArgs, ntt1_body, 128)
 MB_K_NTT(ntt_pass_r4, NttArgs, ntt2_body, 128)
 // The radix-8 pass is latency-bound on its own (152 registers, 12 warps per SM, 45 % of the
-// multiplier: profiles/r01_ncu_ntt_pass_r8.md), but inside the prover that does not show:
-// register-capped variants for 4 / 5 / 6 resident blocks (profiles/r01_ntt_occupancy_sweep.jsonl)
-// and "thin" launches that leave room for accumulation blocks (r01_ntt_thin_sweep.jsonl) were
-// measured at +-0.3 % and -4...-8 % of the proof rate, so the plain kernel stays.
+// multiplier, 6 x the algorithmic HBM traffic: profiles/r01_ncu_ntt_pass_r8.md), which is why the
+// circuits' sizes go through ntt_smem.cuh; this kernel serves the sizes outside 2^12 ... 2^18.
 MB_K_NTT(ntt_pass_r8, NttArgs, ntt3_body, 128)
-inline void launch_ntt_r8(const NttArgs& a, cudaStream_t s) { launch_ntt_pass_r8(a, s); }
 
 // ---------------------------------------------------------------------------
 // domain tables
@@ -188,7 +172,7 @@ inline Fr fr_pow_host(Fr b, uint64_t e) {
 struct NttDomain {
     uint32_t log_n = 0;
     DevBuf tw, cos_fwd, cos_inv, minv_tab;
-    Fr k1, k2;     // zinv * R^2 and zinv * R as stored integers (see header comment)
+    Fr k2;         // 1 / (g^m - 1), Montgomery
     Fr minv;       // Montgomery
 
     void build(uint32_t logn, cudaStream_t s) {
@@ -205,8 +189,7 @@ struct NttDomain {
         Fr ginv = Fr::inv(g);
         minv = Fr::inv(fr_from_u64_host(n));
         Fr zinv = Fr::inv(Fr::sub(fr_pow_host(g, n), Fr::one()));  // 1 / (g^m - 1), Montgomery
-        k2 = zinv;                       // stored integer zinv * R
-        k1 = Fr::mul(zinv, Fr::r2());    // stored integer zinv * R^2
+        k2 = zinv;
         tw.alloc(n * sizeof(Fr));
         cos_fwd.alloc(n * sizeof(Fr));
         cos_inv.alloc(n * sizeof(Fr));
@@ -227,11 +210,10 @@ struct NttDomain {
 struct NttPlan {
     const Fr* in_scale = nullptr;
     const Fr* out_scale = nullptr;
-    const Fr* srcb = nullptr;
-    const Fr* srcc = nullptr;
-    uint32_t src_len = 0;  // 0 = n
+    const Fr* srcb = nullptr;  // plain product with srcb on load
+    uint32_t src_len = 0;      // 0 = n
     bool inverse = false;
-    // six-transform H pipeline: after out_scale, val = (val - sub[o] * sub_k) * post_k on the last store
+    // after out_scale, val = (val - sub[o] * sub_k) * post_k on the last store
     const Fr* sub = nullptr;
     size_t sub_stride = 0;
     Fr sub_k{}, post_k{};
@@ -247,20 +229,13 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
                     size_t dst_stride, Fr* tmp0, Fr* tmp1, cudaStream_t s) {
     uint32_t n = 1u << d.log_n;
     uint32_t left = d.log_n, ns = 1;
-    static const uint32_t max_k = []() {
-        const char* v = getenv("MB200_NTT_RADIX_LOG");
-        uint32_t k = v && *v ? (uint32_t)strtoul(v, nullptr, 10) : 3;
-        return k < 1 ? 1u : (k > 3 ? 3u : k);
-    }();
-    if (ntt_smem_mode() != 0 && ntt_smem_supported(d.log_n)) {
-        // opt-in: two shared-memory kernels (ntt_smem.cuh) instead of the pass loop below
+    if (ntt_smem_supported(d.log_n)) {
+        // two shared-memory kernels (ntt_smem.cuh) instead of the pass loop below
         NttFusedArgs f;
         f.log_n = d.log_n;
         f.inverse = p.inverse ? 1 : 0;
         f.tw = d.tw.as<Fr>();
-        f.k1 = d.k1;
         f.k2 = d.k2;
-        f.bulk_store = (ntt_smem_mode() & 2) ? 1 : 0;
         f.sub = nullptr;
         f.sub_stride = 0;
         f.k3 = d.k2;
@@ -275,7 +250,6 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
         f.src_len = p.src_len ? p.src_len : n;
         f.in_scale = p.in_scale;
         f.srcb = p.srcb;
-        f.srcc = p.srcc;
         f.out_scale = nullptr;
         launch_ntt_fused(f, s);
         f.group = 1;
@@ -289,7 +263,6 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
         f.src_len = n;
         f.in_scale = nullptr;
         f.srcb = nullptr;
-        f.srcc = nullptr;
         f.out_scale = p.out_scale;
         if (p.sub) {
             f.sub = p.sub;
@@ -305,7 +278,7 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
     int flip = 0;
     bool first = true;
     while (left) {
-        uint32_t K = left >= max_k ? max_k : left;
+        uint32_t K = left >= 3 ? 3 : left;
         bool last = left == K;
         NttArgs a;
         a.nthreads = (size_t)batch * (n >> K);
@@ -321,19 +294,11 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
         a.in_scale = first ? p.in_scale : nullptr;
         a.out_scale = last ? p.out_scale : nullptr;
         a.srcb = first ? p.srcb : nullptr;
-        a.srcc = first ? p.srcc : nullptr;
-        a.k1 = d.k1;
-        a.k2 = d.k2;
+        a.k2 = p.post_k;
         a.sub = last ? p.sub : nullptr;
         a.sub_stride = p.sub_stride;
         a.k3 = p.sub_k;
-        const bool ext = (a.srcb && !a.srcc) || a.sub;   // six-transform H pipeline only
-        if (a.sub) a.k2 = p.post_k;
-        if (ext) {
-            if (K == 3) launch_ntt_pass_r8_ext(a, s);
-            else if (K == 2) launch_ntt_pass_r4_ext(a, s);
-            else launch_ntt_pass_r2_ext(a, s);
-        } else if (K == 3) launch_ntt_r8(a, s);
+        if (K == 3) launch_ntt_pass_r8(a, s);
         else if (K == 2) launch_ntt_pass_r4(a, s);
         else launch_ntt_pass_r2(a, s);
         cur = a.dst;
@@ -350,6 +315,13 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
 // the m coefficients of each proof's quotient to hout + proof * hout_stride (the
 // caller ignores coefficient m-1, as bellman truncates it).
 // work0..work3: scratch of batch * 3 * m elements each.
+//
+// SIX transforms where bellman runs seven (3 ifft, 3 coset_fft, 1 icoset_fft): the inverse coset
+// transform is linear, so
+//   icoset[(a b - c)(g w^i) / (g^m - 1)] = (icoset[(a b)(g w^i)] - c(X)) / (g^m - 1)
+// coefficient by coefficient, and c(X) is already there after step 1: the coset transform of c
+// is never needed.  Same field elements as the seven-transform form for ANY rows (satisfied or
+// not), hence the same proof bytes (tests/test_emu.py, tests/test_gpu_parity.py::test_h_*).
 inline void h_pipeline(const NttDomain& d, uint32_t batch, uint32_t rows, const Fr* abc, size_t poly_stride,
                        Fr* hout, size_t hout_stride, Fr* work0, Fr* work1, Fr* work2, Fr* work3, cudaStream_t s) {
     uint32_t n = 1u << d.log_n;
@@ -358,44 +330,22 @@ inline void h_pipeline(const NttDomain& d, uint32_t batch, uint32_t rows, const 
     p1.inverse = true;
     p1.src_len = rows;
     ntt_run(d, p1, batch * 3, abc, poly_stride, work2, n, work0, work1, s);
-    static const bool six_env = [] {
-        const char* e = getenv("MB200_H_SIX");
-        return e && *e && *e != '0';
-    }();
-    if (six_env || ((ntt_smem_mode() & 4) && ntt_smem_supported(d.log_n))) {
-        // Opt-in (MB200_H_SIX=1 with either NTT path, or MB200_NTT_SMEM=5|7): SIX transforms.  The inverse coset transform is linear, so
-        //   icoset[(a b - c)(g w^i) / (g^m - 1)] = (icoset[(a b)(g w^i)] - c(X)) / (g^m - 1)
-        // coefficient by coefficient, and c(X) is already there after step 1: the coset transform
-        // of c is never needed.  Same field elements as the seven-transform form for ANY rows
-        // (satisfied or not), hence the same proof bytes.
-        NttPlan q2;
-        q2.in_scale = d.cos_fwd.as<Fr>();
-        for (uint32_t poly = 0; poly < 2; ++poly)   // a and b only; polynomials of a proof sit n apart
-            ntt_run(d, q2, batch, work2 + (size_t)poly * n, 3 * (size_t)n, work3 + (size_t)poly * n, 3 * (size_t)n, work0,
-                    work1, s);
-        NttPlan q3;
-        q3.inverse = true;
-        q3.srcb = work3 + n;            // plain product a * b on load
-        q3.out_scale = d.cos_inv.as<Fr>();   // g^-i / m
-        q3.sub = work2 + 2 * (size_t)n;      // raw inverse transform of c: still lacks its 1/m
-        q3.sub_stride = 3 * (size_t)n;
-        q3.sub_k = d.minv;
-        q3.post_k = d.k2;               // 1 / (g^m - 1), Montgomery form
-        ntt_run(d, q3, batch, work3, 3 * (size_t)n, hout, hout_stride, work0, work1, s);
-        return;
-    }
-    // 2. coset forward transforms; 1/m and g^i folded into the load
-    NttPlan p2;
-    p2.in_scale = d.cos_fwd.as<Fr>();
-    ntt_run(d, p2, batch * 3, work2, n, work3, n, work0, work1, s);
-    // 3. (a*b - c)/Z on load, inverse transform, 1/m and g^-i on store.
-    //    Items are the proofs; a, b, c of a proof sit n apart.
-    NttPlan p3;
-    p3.inverse = true;
-    p3.srcb = work3 + n;
-    p3.srcc = work3 + 2 * (size_t)n;
-    p3.out_scale = d.cos_inv.as<Fr>();
-    ntt_run(d, p3, batch, work3, 3 * (size_t)n, hout, hout_stride, work0, work1, s);
+    // 2. coset forward transforms of a and b; 1/m and g^i folded into the load
+    NttPlan q2;
+    q2.in_scale = d.cos_fwd.as<Fr>();
+    for (uint32_t poly = 0; poly < 2; ++poly)  // polynomials of a proof sit n apart
+        ntt_run(d, q2, batch, work2 + (size_t)poly * n, 3 * (size_t)n, work3 + (size_t)poly * n, 3 * (size_t)n, work0,
+                work1, s);
+    // 3. a * b on load, inverse transform; g^-i / m, - c(X) and 1 / (g^m - 1) on the last store
+    NttPlan q3;
+    q3.inverse = true;
+    q3.srcb = work3 + n;
+    q3.out_scale = d.cos_inv.as<Fr>();
+    q3.sub = work2 + 2 * (size_t)n;  // raw inverse transform of c: still lacks its 1/m
+    q3.sub_stride = 3 * (size_t)n;
+    q3.sub_k = d.minv;
+    q3.post_k = d.k2;
+    ntt_run(d, q3, batch, work3, 3 * (size_t)n, hout, hout_stride, work0, work1, s);
 }
 
 }  // namespace mb

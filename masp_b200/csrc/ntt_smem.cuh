@@ -1,7 +1,8 @@
 // Shared-memory formulation of the Stockham NTT: two kernels instead of six passes.
 //
-// OPT-IN (MB200_NTT_SMEM=1, =2 adds the TMA bulk store, =5 / =7 the six-transform H pipeline); bit-identical to the pass-per-launch
-// path of ntt.cuh (tests/test_emu.py runs both), not yet measured on a B200 -- see DESIGN.md §4.1.
+// The default for 2^12 <= n <= 2^18 (every MASP circuit): measured on B200 at 492 -> 517 Spend
+// proofs/s against the pass-per-launch kernels (profiles/r02_variants_ab.jsonl), bit-identical
+// to them (tests/test_emu.py runs both forms on the same data).
 //
 // The first three radix-8 passes of the autosort transform of size n are, for every residue
 // g mod n/512, one 512-point transform over the elements g + s * n/512, whose result lands in
@@ -10,9 +11,9 @@
 // in place.  So:
 //
 //   kernel 1 (group 0)  gathers C = 4 such 512-point problems (128-byte segments), runs three
-//                       radix-8 passes in shared memory and writes four contiguous 16 KB runs
-//                       -- with MB200_NTT_SMEM=2 as one TMA bulk copy each
-//                       (cp.async.bulk.global.shared::cta), the one contiguous tile on this path;
+//                       radix-8 passes in shared memory and writes four contiguous 16 KB runs,
+//                       each as one TMA bulk copy (cp.async.bulk.global.shared::cta; SASS UBLKCP.G.S),
+//                       the one contiguous tile on this path;
 //   kernel 2 (group 1)  gathers C = 2048 / (n/512) problems of size n/512 (32 C-byte segments),
 //                       runs the remaining passes (radix 8, 8 and a tail of 4 or 2) in shared
 //                       memory and scatters with the same pattern.
@@ -34,16 +35,14 @@ struct NttFusedArgs {
     const Fr* src;
     Fr* dst;
     size_t src_stride, dst_stride;
-    uint32_t src_len, log_n, L, logC, group, inverse, bulk_store;
+    uint32_t src_len, log_n, L, logC, group, inverse;
     const Fr* tw;
     const Fr* in_scale;
     const Fr* out_scale;
-    const Fr* srcb;
-    const Fr* srcc;       // nullptr with srcb set: plain product a * b on load
-    Fr k1, k2;
+    const Fr* srcb;       // plain product a * b on load
     const Fr* sub;        // optional, group 1 store: val = (val - sub[idx] * k3) * k2
     size_t sub_stride;
-    Fr k3;
+    Fr k2, k3;
 };
 
 static const uint32_t NTT_SMEM_ELEMS = 2048, NTT_SMEM_THREADS = 256, NTT_SMEM_L1 = 9;
@@ -168,23 +167,15 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
             Fr x = Fr::zero();
             if (idx < a.src_len) {
                 x = src[idx];
-                if (a.srcb) {
-                    Fr b = a.srcb[item * a.src_stride + idx];
-                    if (a.srcc) {
-                        Fr cc = a.srcc[item * a.src_stride + idx];
-                        x = Fr::sub(Fr::mul(Fr::mul(x, b), a.k1), Fr::mul(cc, a.k2));
-                    } else {
-                        x = Fr::mul(Fr::mul(x, b), Fr::r2());
-                    }
-                }
+                if (a.srcb) x = Fr::mul(Fr::mul(x, a.srcb[item * a.src_stride + idx]), Fr::r2());
                 if (a.in_scale) x = Fr::mul(x, a.in_scale[idx]);
             }
             sm[c * Lp + ntt_slot(s, false)] = x;
         }
     }
     MB_BLOCK_SYNC();
-    // the last pass of kernel 1 leaves natural order when the TMA bulk store follows
-    const bool nat_out = a.group == 0 && a.bulk_store;
+    // the last pass of kernel 1 leaves natural order: the TMA bulk store copies the arrays as they lie
+    const bool nat_out = a.group == 0;
     uint32_t left = a.L, ns = 1;
     while (left >= 3) {
         ntt_fused_pass<3>(a, sm, regs, g0, ns, nat_out && left == 3);
@@ -196,26 +187,23 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
     if (a.group == 0) {
         // array c is the contiguous run dst[(g0 + c) * 2^L ...]
 #ifndef MB200_EMU
-        if (a.bulk_store) {
-            // TMA: one bulk copy per array, all issued by one thread; the generic-proxy writes of the
-            // last pass are made visible to the async proxy first.
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                MB_NOUNROLL
-                for (uint32_t c = 0; c < C; ++c) {
-                    uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sm + c * Lp);
-                    Fr* gptr = dst + (size_t)(g0 + c) * Ln;
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr),
-                                 "r"(saddr), "r"(Ln * (uint32_t)sizeof(Fr))
-                                 : "memory");
-                }
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        // TMA: one bulk copy per array, all issued by one thread; the generic-proxy writes of the
+        // last pass are made visible to the async proxy first.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            MB_NOUNROLL
+            for (uint32_t c = 0; c < C; ++c) {
+                uint32_t saddr = (uint32_t)__cvta_generic_to_shared(sm + c * Lp);
+                Fr* gptr = dst + (size_t)(g0 + c) * Ln;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gptr),
+                             "r"(saddr), "r"(Ln * (uint32_t)sizeof(Fr))
+                             : "memory");
             }
-            return;
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-#endif
+#else
         MB_FOR_THREADS(t) {
             MB_UNROLL
             for (int i = 0; i < 8; ++i) {
@@ -224,6 +212,7 @@ MB_BLOCK_FN void ntt_fused_block(const NttFusedArgs& a, size_t blk, Fr* sm, Fr (
                 dst[(size_t)(g0 + c) * Ln + k] = sm[c * Lp + ntt_slot(k, nat_out)];
             }
         }
+#endif
     } else {
         MB_FOR_THREADS(t) {
             MB_UNROLL
@@ -262,12 +251,11 @@ __global__ void __launch_bounds__(NTT_SMEM_THREADS, 2) ntt_fused(const NttFusedA
 }
 void launch_ntt_fused(const NttFusedArgs& a, cudaStream_t s) {
     if (!a.nblocks) return;
-    static const bool attr = [] {
+    static std::atomic<unsigned long long> attr_done{0};
+    once_per_device(attr_done, [] {
         MB_CUDA(cudaFuncSetAttribute(ntt_fused, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(NTT_SMEM_ALLOC * sizeof(Fr))));
-        return true;
-    }();
-    (void)attr;
+    });
     ntt_fused<<<(unsigned)a.nblocks, NTT_SMEM_THREADS, NTT_SMEM_ALLOC * sizeof(Fr), s>>>(a);
     MB_CUDA(cudaGetLastError());
     ::mb::g_launches++;
@@ -277,18 +265,6 @@ void launch_ntt_fused(const NttFusedArgs& a, cudaStream_t s);
 #endif
 #endif
 
-// 0: pass-per-launch path (default).  Bit 0: shared-memory kernels; value 2 or bit 1 with bit 0: TMA bulk
-// store in kernel 1; bit 2 (with bit 0): the H pipeline with six transforms instead of seven (ntt.cuh).
-// So 1 = smem, 2 or 3 = smem + TMA, 5 = smem + six transforms, 7 = all three.
-inline uint32_t ntt_smem_mode() {
-    static const uint32_t v = [] {
-        const char* e = getenv("MB200_NTT_SMEM");
-        uint32_t m = (e && *e) ? (uint32_t)strtoul(e, nullptr, 10) : 0u;
-        if (m == 2) m = 3;
-        return (m & 1) ? m : 0u;
-    }();
-    return v;
-}
 inline bool ntt_smem_supported(uint32_t log_n) { return log_n >= NTT_SMEM_L1 + 3 && log_n <= 2 * NTT_SMEM_L1; }
 
 }  // namespace mb

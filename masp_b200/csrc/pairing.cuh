@@ -455,6 +455,8 @@ MB_HD void proof_read_body(const ProofReadArgs& a, size_t tid) {
     if (which == 0) ok = g1_decode_compressed(p, a.pa[proof]);
     else if (which == 1) ok = g2_decode_compressed(p + 48, a.pb[proof]);
     else ok = g1_decode_compressed(p + 144, a.pc[proof]);
+    // bellman's Proof::read: "point at infinity" is an error for A, B and C alike
+    if (ok) ok = which == 1 ? !a.pb[proof].is_inf() : (which == 0 ? !a.pa[proof].is_inf() : !a.pc[proof].is_inf());
     if (!ok) {
         if (which == 0) a.pa[proof] = G1Affine::inf();
         else if (which == 1) a.pb[proof] = G2Affine::inf();
@@ -494,7 +496,10 @@ MB_HD void batch_miller_body(const BatchMillerArgs& a, size_t tid) {
     for (int i = 0; i < 8; ++i) zf.v[i] = k[i];
     Fr zm = Fr::from_std(zf);  // Montgomery form: montmul(x, z R) = x z on plain x
     const Fr* x = (const Fr*)(a.inputs + tid * (size_t)a.n_inputs * 8);
-    for (uint32_t j = 0; j < a.n_inputs; ++j) a.zx[tid * (size_t)a.n_inputs + j] = Fr::mul(x[j], zm);
+    // column 0 is the constant ONE whatever the caller stored there (verify_body ignores it too):
+    // both entry points must give the same verdict on the same bytes
+    a.zx[tid * (size_t)a.n_inputs] = zf;
+    for (uint32_t j = 1; j < a.n_inputs; ++j) a.zx[tid * (size_t)a.n_inputs + j] = Fr::mul(x[j], zm);
 }
 struct BatchFinalArgs {
     size_t nthreads;  // 1

@@ -34,6 +34,8 @@ struct DecodeArgs {
     const uint8_t* src;   // nthreads encodings, 96 (G1) or 192 (G2) bytes each
     void* dst;            // Affine<F>[nthreads]
     uint32_t* bad;        // set to 1 on a malformed encoding
+    uint32_t reject_inf = 0;  // 1: the identity is malformed too -- bellman's read_g1 / read_g2 closures in
+                              // Parameters::read and VerifyingKey::read fail with "point at infinity" even unchecked
 };
 MB_HD void decode_g1_body(const DecodeArgs& a, size_t tid) {
     G1Affine p;
@@ -41,6 +43,7 @@ MB_HD void decode_g1_body(const DecodeArgs& a, size_t tid) {
         *a.bad = 1;
         p = G1Affine::inf();
     }
+    if (a.reject_inf && p.is_inf()) *a.bad = 1;
     ((G1Affine*)a.dst)[tid] = p;
 }
 MB_HD void decode_g2_body(const DecodeArgs& a, size_t tid) {
@@ -49,6 +52,7 @@ MB_HD void decode_g2_body(const DecodeArgs& a, size_t tid) {
         *a.bad = 1;
         p = G2Affine::inf();
     }
+    if (a.reject_inf && p.is_inf()) *a.bad = 1;
     ((G2Affine*)a.dst)[tid] = p;
 }
 MB_K_G1(decode_g1, DecodeArgs, decode_g1_body, 128)
@@ -198,7 +202,18 @@ struct Params {
     DevBuf vk_g1, vk_g2, vk_ic, vk_ab;  // alpha_g1 | beta, gamma, delta (G2) | IC | Miller(-alpha, beta): the self-check
     R1csDev r1cs;                   // the circuit's matrices, when one is bound (mb200_params_bind_circuit)
     size_t table_bytes = 0;
+    // the density bitmaps the key was loaded with (empty = all dense): mb200_params_bind_circuit
+    // compares them with the circuit's, position by position
+    std::vector<uint8_t> a_aux_density, b_input_density, b_aux_density;
 };
+inline bool density_equal(const std::vector<uint8_t>& loaded, const std::vector<uint8_t>& want, size_t nbits) {
+    for (size_t i = 0; i < nbits; ++i) {
+        bool w = (want[i >> 3] >> (i & 7)) & 1;
+        bool l = loaded.empty() ? true : ((loaded[i >> 3] >> (i & 7)) & 1);
+        if (w != l) return false;
+    }
+    return true;
+}
 
 static inline bool bm_bit(const uint8_t* bm, size_t i) { return (bm[i >> 3] >> (i & 7)) & 1; }
 static inline uint32_t be32(const uint8_t* p) {
@@ -282,6 +297,9 @@ inline Params* params_load(const uint8_t* buf, size_t len, const uint8_t* a_aux_
     if (n_b1 != b_in_sel.size() + b_sel.size())
         fail(MB200_EINVAL, "b query length does not match the b densities%s (%ld bases)", "", (long)n_b1);
     P->n_b_inputs = (uint32_t)b_in_sel.size();
+    if (a_aux_density) P->a_aux_density.assign(a_aux_density, a_aux_density + (n_l + 7) / 8);
+    if (b_input_density) P->b_input_density.assign(b_input_density, b_input_density + (n_ic + 7) / 8);
+    if (b_aux_density) P->b_aux_density.assign(b_aux_density, b_aux_density + (n_l + 7) / 8);
 
     P->idx_aux = m;
     P->idx_inputs = (size_t)m + n_l;
@@ -321,11 +339,11 @@ inline Params* params_load(const uint8_t* buf, size_t len, const uint8_t* a_aux_
     DevBuf b_hl((size_t)(n_h + n_l) * sizeof(G1Affine)), b_a((size_t)(n_a + 2) * sizeof(G1Affine)),
         b_b1((size_t)(n_b1 + 1) * sizeof(G1Affine)), b_b2((size_t)(n_b2 + 2) * sizeof(G2Affine));
     auto dec1 = [&](size_t off, uint32_t n, G1Affine* dst) {
-        DecodeArgs a{n, rb + off, dst, bad.as<uint32_t>()};
+        DecodeArgs a{n, rb + off, dst, bad.as<uint32_t>(), 1};
         launch_decode_g1(a, s);
     };
     auto dec2 = [&](size_t off, uint32_t n, G2Affine* dst) {
-        DecodeArgs a{n, rb + off, dst, bad.as<uint32_t>()};
+        DecodeArgs a{n, rb + off, dst, bad.as<uint32_t>(), 1};
         launch_decode_g2(a, s);
     };
     // VerifyingKey: alpha_g1 0, beta_g1 96, beta_g2 192, gamma_g2 384, delta_g1 576, delta_g2 672
@@ -378,14 +396,11 @@ inline Params* params_load(const uint8_t* buf, size_t len, const uint8_t* a_aux_
 struct ProveCtx {  // one in-flight chunk: its streams and scratch
     cudaStream_t stream = 0;      // copies, NTT, H+L MSM, assembly
     cudaStream_t side[3] = {0, 0, 0};  // A, B1, B2 MSMs: they need only the staged witness, not the NTT
-    cudaStream_t tail[4] = {0, 0, 0, 0};  // high priority: reduction tails of A, B1, B2; [3] = H+L tail, assembly
-    bool split_tail = false;
     DevBuf abc, w0, w1, w2, w3, pool, flag, res_hl, res_a, res_b1, res_b2, cmul, proofs;
     MsmScratch msm, msm_side[3];
     bool have_stream = false;
 #ifndef MB200_EMU
-    cudaEvent_t ev_inputs = nullptr, ev_side[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_acc[4] = {nullptr, nullptr, nullptr, nullptr}, ev_tail = nullptr;
+    cudaEvent_t ev_inputs = nullptr, ev_side[3] = {nullptr, nullptr, nullptr}, ev_tail = nullptr;
 #endif
 };
 
@@ -485,32 +500,20 @@ inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, siz
     MB_CUDA(cudaEventRecord(x.ev_inputs, s));
     for (int i = 0; i < 3; ++i) MB_CUDA(cudaStreamWaitEvent(x.side[i], x.ev_inputs, 0));
 #endif
-    MsmTail t_a, t_b1, t_b2, t_hl;
-    cudaStream_t fin = s;  // where the assembly runs
-#ifndef MB200_EMU
-    if (x.split_tail) {
-        t_a = {x.tail[0], x.ev_acc[0]};
-        t_b1 = {x.tail[1], x.ev_acc[1]};
-        t_b2 = {x.tail[2], x.ev_acc[2]};
-        t_hl = {x.tail[3], x.ev_acc[3]};
-        fin = x.tail[3];
-    }
-#endif
-    msm_run<Fp>(P.k_a, count, pl, P.pool_stride, x.res_a.as<G1XYZZ>(), x.msm_side[0], x.side[0], t_a);
-    msm_run<Fp>(P.k_b1, count, pl, P.pool_stride, x.res_b1.as<G1XYZZ>(), x.msm_side[1], x.side[1], t_b1);
-    msm_run<Fp2>(P.k_b2, count, pl, P.pool_stride, x.res_b2.as<G2XYZZ>(), x.msm_side[2], x.side[2], t_b2);
+    msm_run<Fp>(P.k_a, count, pl, P.pool_stride, x.res_a.as<G1XYZZ>(), x.msm_side[0], x.side[0]);
+    msm_run<Fp>(P.k_b1, count, pl, P.pool_stride, x.res_b1.as<G1XYZZ>(), x.msm_side[1], x.side[1]);
+    msm_run<Fp2>(P.k_b2, count, pl, P.pool_stride, x.res_b2.as<G2XYZZ>(), x.msm_side[2], x.side[2]);
 
     h_pipeline(P.dom, count, (uint32_t)rows, x.abc.as<Fr>(), rows, x.pool.as<Fr>(), P.pool_stride, x.w0.as<Fr>(),
                x.w1.as<Fr>(), x.w2.as<Fr>(), x.w3.as<Fr>(), s);
-    msm_run<Fp>(P.k_hl, count, pl, P.pool_stride, x.res_hl.as<G1XYZZ>(), x.msm, s, t_hl);
-    // join: the assembly stream waits for the three side queries
+    msm_run<Fp>(P.k_hl, count, pl, P.pool_stride, x.res_hl.as<G1XYZZ>(), x.msm, s);
+    // join: the assembly waits for the three side queries
 #ifndef MB200_EMU
     for (int i = 0; i < 3; ++i) {
-        MB_CUDA(cudaEventRecord(x.ev_side[i], x.split_tail ? x.tail[i] : x.side[i]));
-        MB_CUDA(cudaStreamWaitEvent(fin, x.ev_side[i], 0));
+        MB_CUDA(cudaEventRecord(x.ev_side[i], x.side[i]));
+        MB_CUDA(cudaStreamWaitEvent(s, x.ev_side[i], 0));
     }
 #endif
-    s = fin;
 
     CmulArgs ca{(size_t)count * 2, x.res_a.as<G1XYZZ>(), x.res_b1.as<G1XYZZ>(), pl, P.pool_stride, P.idx_r, P.idx_s,
                 x.cmul.as<G1XYZZ>()};
@@ -549,12 +552,6 @@ inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, siz
         launch_verify_proofs(va, v);
         copy_d2h(vs.ok_host + first, va.ok, (size_t)count * 4, v);
     }
-#ifndef MB200_EMU
-    if (x.split_tail) {  // the chunk is done when its tail is: later work on this context queues behind it
-        MB_CUDA(cudaEventRecord(x.ev_acc[3], s));
-        MB_CUDA(cudaStreamWaitEvent(x.stream, x.ev_acc[3], 0));
-    }
-#endif
 }
 
 }  // namespace mb

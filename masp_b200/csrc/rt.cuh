@@ -7,6 +7,7 @@
 //     (tests/emu/); it is never loaded by the masp_b200 package and is not a
 //     fallback of any product path.
 #pragma once
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>
@@ -52,7 +53,7 @@ struct Exc {
     throw Exc{code};
 }
 
-extern unsigned long long g_launches;  // kernels launched by this library (bench "gpu_launches")
+extern std::atomic<unsigned long long> g_launches;  // kernels launched by this library, all devices (bench "gpu_launches")
 
 #ifndef MB200_EMU
 #define MB_CUDA(x)                                                                       \
@@ -60,6 +61,17 @@ extern unsigned long long g_launches;  // kernels launched by this library (benc
         cudaError_t _e = (x);                                                            \
         if (_e != cudaSuccess) ::mb::fail(MB200_ECUDA, "CUDA: %s (line %ld)", cudaGetErrorString(_e), __LINE__); \
     } while (0)
+
+// cudaFuncSetAttribute is per device: run `f` the first time each device reaches a launch site.
+template <class Fn>
+inline void once_per_device(std::atomic<unsigned long long>& done, Fn f) {
+    int dev = 0;
+    MB_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return;
+    f();
+    done.fetch_or(bit, std::memory_order_release);
+}
 
 // One thread per work item; Args carries `size_t nthreads`.  Every kernel is
 // declared wherever its header is included and defined in exactly one

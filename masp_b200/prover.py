@@ -44,15 +44,34 @@ _initialised = False
 
 
 def init(device=None):
-    """Bind this process to one GPU (default: the current CUDA device)."""
+    """Open the GPU(s) this process drives: None = the current CUDA device, an int = that
+    device, a list = those devices (the first is the primary one), "all" = every visible device.
+    With several devices a key is replicated to each and every batch is cut into per-device
+    slices inside the library (one prover object for the whole process, like the reference's
+    LocalTxProver behind `&self`, masp_proofs/src/prover.rs:27-33, 156-261)."""
     global _initialised
     L = _lib.lib()
     if device is None:
         check(L.mb200_init(None, 0))
+    elif device == "all":
+        check(L.mb200_init(None, -1))
+    elif isinstance(device, (list, tuple)):
+        ids = (ctypes.c_int * len(device))(*[int(d) for d in device])
+        check(L.mb200_init(ids, len(device)))
     else:
         ids = (ctypes.c_int * 1)(int(device))
         check(L.mb200_init(ids, 1))
     _initialised = True
+
+
+def shutdown():
+    global _initialised
+    check(_lib.lib().mb200_shutdown())
+    _initialised = False
+
+
+def device_count():
+    return int(_lib.lib().mb200_device_count())
 
 
 def _ensure_init():
@@ -79,6 +98,8 @@ def _ptr(x):
         return ctypes.c_void_p(x)
     if isinstance(x, (bytes, bytearray)):
         return ctypes.cast(ctypes.c_char_p(bytes(x)) if isinstance(x, bytearray) else ctypes.c_char_p(x), ctypes.c_void_p)
+    if isinstance(x, ctypes.Array):
+        return ctypes.cast(x, ctypes.c_void_p)
     if hasattr(x, "ctypes"):  # numpy array
         return ctypes.c_void_p(x.ctypes.data)
     if hasattr(x, "data_ptr"):  # torch tensor
@@ -480,6 +501,12 @@ class G1Bases:
                                               ctypes.cast(out, ctypes.c_void_p)))
         return out.raw
 
+    def msm_partial_into(self, scalars, dev_partial, n=None):
+        """Same, the 192-byte XYZZ partial written to device memory (an address or a CUDA
+        tensor): the buffer an all-gather sends, no host hop."""
+        check(_lib.lib().mb200_msm_g1_partial_device(self._p, _ptr(scalars), self.n if n is None else n,
+                                                     _ptr(dev_partial)))
+
     def __del__(self):
         p = getattr(self, "_p", None)
         if p:
@@ -488,6 +515,41 @@ class G1Bases:
             except Exception:
                 pass
             self._p = None
+
+
+class SplitG1Bases:
+    """Bases of one large MSM range-split over every device this process opened
+    (BASELINE config 3 in one process): msm() reduces each range on its GPU, gathers the
+    192-byte partials GPU -> GPU on the primary device and adds them there."""
+
+    def __init__(self, bases, n):
+        _ensure_init()
+        self.n = n
+        self._h = ctypes.c_void_p()
+        check(_lib.lib().mb200_g1_bases_new(_ptr(bases), n, ctypes.byref(self._h)))
+
+    def msm(self, scalars):
+        out = ctypes.create_string_buffer(96)
+        check(_lib.lib().mb200_msm_g1_bases(self._h, _ptr(scalars), self.n, ctypes.cast(out, ctypes.c_void_p)))
+        return out.raw
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().mb200_g1_bases_free(h)
+            except Exception:
+                pass
+            self._h = None
+
+
+def g1_sum_partials_device(dev_partials, count):
+    """Adds `count` XYZZ partials that sit in device memory (e.g. the output of an
+    NCCL all-gather) on the device and returns the uncompressed sum."""
+    _ensure_init()
+    out = ctypes.create_string_buffer(96)
+    check(_lib.lib().mb200_g1_sum_partials_device(_ptr(dev_partials), count, ctypes.cast(out, ctypes.c_void_p)))
+    return out.raw
 
 
 def g1_sum_partials(partials):

@@ -15,7 +15,7 @@ fi
 
 if [ "$what" = ab ] || [ "$what" = all ]; then
   : > gpurun_out/variants_ab.jsonl
-  for cfg in "0 0" "1 0" "3 0" "4 0" "2 0" "0 g1" "0 g2" "0 g12" "0 six" "0 1" "0 2" "0 5" "1 six" "0 0" "1 0" "4 0" "0 g1" "0 g12" "0 six"; do
+  for cfg in "0 0" "1 0" "3 0" "4 0" "0 g1" "0 g2" "0 g12" "0 six" "0 1" "0 2" "0 5" "0 7" "0 0" "1 0" "0 g2" "0 six" "0 2"; do
     set -- $cfg; ls=$1; ns=$2; six=0; g1=0; g2=0
     case "$ns" in six) ns=0; six=1;; g1) ns=0; g1=1;; g2) ns=0; g2=1;; g12) ns=0; g1=1; g2=1;; esac
     MB200_ACC_LOCKSTEP=$ls MB200_NTT_SMEM=$ns MB200_H_SIX=$six MB200_ACC_G1_SMEM=$g1 MB200_ACC_G2_SMEM=$g2 \

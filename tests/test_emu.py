@@ -93,9 +93,8 @@ def test_local_tx_prover_surface(emu, oracle):
 
 
 def test_msm_special_bases(emu, oracle):
-    """Repeated bases (P + P inside a pair), negated pairs (P + (-P)), identities:
-    the shared-inversion pair rounds (csrc/pair.cuh) must take the tangent, drop
-    the cancelling pair and pass infinities through, like the XYZZ accumulator."""
+    """Repeated bases (P + P), negated pairs (P + (-P)), identities: the XYZZ accumulator
+    must take the tangent, drop the cancelling pair and pass infinities through."""
     P_MOD = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
     logs = syn.fr_uniform(syn.MASTER_SEED, 12, 8)
     bases = oracle.g1_gen_mul(syn.limbs_to_bytes(logs), 8)
@@ -115,79 +114,27 @@ def test_msm_special_bases(emu, oracle):
 
 
 @pytest.mark.slow
-def test_pair_rounds_variant():
-    """The opt-in batched-affine pair rounds (csrc/pair.cuh, MB200_PAIR_ROUNDS) give the
-    same bytes as the default schedule: the MSM and prover tests again in a child
-    process with the rounds switched on (the knob is read once per process)."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, MB200_PAIR_ROUNDS="3", MB200_PASS_INSTANCES="2", MB200_PAIR_B="5")
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_emu.py"), "-x", "-q", "-k",
-                        "test_msm or test_prove_batch_chunked"], env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-2000:]
-
-
-_NTT_SMEM_CHILD = r"""
-import hashlib, sys
-sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
-from util import load_emu, ib, rand_scalars
-emu = load_emu()
-for log_n in (11, 12, 16, 17):
-    v = ib(rand_scalars(1 << log_n, log_n, "uniform"))
-    for inv in (False, True):
-        for cos in (False, True):
-            l0 = emu.get_counter("launches")
-            out = emu.ntt(v, log_n, inv, cos)
-            print("ntt", log_n, int(inv), int(cos), hashlib.sha256(out).hexdigest(), "launches", int(emu.get_counter("launches") - l0))
-for rows in (2049, 31211):
-    a, b = ib(rand_scalars(rows, 1, "uniform")), ib(rand_scalars(rows, 2, "uniform"))
-    c = emu.fr_mul(a, b, rows)
-    print("h", rows, hashlib.sha256(emu.h_coeffs(a, b, c, rows)).hexdigest())
-    c = ib(rand_scalars(rows, 3))      # unsatisfied rows: the division by Z is not exact
-    print("h", -rows, hashlib.sha256(emu.h_coeffs(a, b, c, rows)).hexdigest())
-"""
-
-
-@pytest.mark.slow
-def test_ntt_shared_memory_variant():
-    """The opt-in two-kernel shared-memory NTT (csrc/ntt_smem.cuh, MB200_NTT_SMEM=1) against the
-    pass-per-launch path: same bytes for every mode (forward / inverse, coset or not) at sizes on both
-    sides of its range (2^12 .. 2^18), and through the fused H pipeline (2^12 and the Output size 2^15,
-    satisfied and unsatisfied rows, with seven transforms and with six) -- and it really is two launches where the default path needs four to six."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    runs = {}
-    envs = {"0": {"MB200_NTT_SMEM": "0"}, "1": {"MB200_NTT_SMEM": "1"}, "5": {"MB200_NTT_SMEM": "5"},
-            "3": {"MB200_NTT_SMEM": "3"},   # natural-order output of kernel 1 (the layout its TMA bulk store reads)
-            "six": {"MB200_NTT_SMEM": "0", "MB200_H_SIX": "1"}}
-    procs = {mode: subprocess.Popen([sys.executable, "-c", _NTT_SMEM_CHILD, root], env=dict(os.environ, **extra),
-                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-             for mode, extra in envs.items()}
-    for mode, pr in procs.items():
-        out, err = pr.communicate(timeout=900)
-        assert pr.returncode == 0, err[-2000:]
-        runs[mode] = [l.split() for l in out.strip().splitlines()]
-    assert len(runs["0"]) == len(runs["1"]) == len(runs["5"]) == len(runs["3"]) == 4 * 4 + 4
-    assert [l[:5] for l in runs["3"]] == [l[:5] for l in runs["0"]]
-    # mode 5: the H pipeline with six transforms (the coset transform of c is never needed because the
-    # inverse coset transform is linear): same coefficients for satisfied AND unsatisfied rows
-    assert [l for l in runs["5"] if l[0] == "h"] == [l for l in runs["0"] if l[0] == "h"]
-    assert [l[:5] for l in runs["six"]] == [l[:5] for l in runs["0"]]   # MB200_H_SIX=1 on the default kernels
-    for base, smem in zip(runs["0"], runs["1"]):
-        if base[0] == "h":
-            assert base == smem
-            continue
-        assert base[:5] == smem[:5], base[:4]          # same digest
-        log_n = int(base[1])
-        # the coset modes add a scaling launch in front / behind; the transform itself:
-        if 12 <= log_n <= 18:
-            assert int(base[-1]) - int(smem[-1]) == (log_n + 2) // 3 - 2, (base, smem)
-        else:
-            assert base[-1] == smem[-1]
+def test_ntt_shared_memory_form(emu, oracle):
+    """The two-kernel shared-memory NTT (csrc/ntt_smem.cuh: every size from 2^12 to 2^18) and the
+    pass-per-launch kernels (sizes outside that range) against the oracle: every mode (forward /
+    inverse, coset or not) at sizes on both sides of the boundary, and through the six-transform H
+    pipeline at 2^12 and the Output size 2^15 -- for satisfied rows AND for unsatisfied ones, where
+    the division by Z is not exact (the six-transform identity must hold coefficient by coefficient
+    for any rows) -- and it really is two launches where the pass form needs four to six."""
+    for log_n in (11, 12, 16, 17):
+        v = ib(rand_scalars(1 << log_n, log_n, "uniform"))
+        for inv in (False, True):
+            for cos in (False, True):
+                l0 = emu.get_counter("launches")
+                assert emu.ntt(v, log_n, inv, cos) == oracle.ntt(v, log_n, inv, cos), (log_n, inv, cos)
+                launches = int(emu.get_counter("launches") - l0) - 1      # minus the scalar range check
+                assert launches == (2 if log_n >= 12 else (log_n + 2) // 3), (log_n, launches)
+    for rows in (2049, 31211):
+        a, b = ib(rand_scalars(rows, 1, "uniform")), ib(rand_scalars(rows, 2, "uniform"))
+        c = emu.fr_mul(a, b, rows)
+        assert emu.h_coeffs(a, b, c, rows) == oracle.h_coeffs(a, b, c, rows), rows
+        c = ib(rand_scalars(rows, 3))
+        assert emu.h_coeffs(a, b, c, rows) == oracle.h_coeffs(a, b, c, rows), -rows
 
 
 @pytest.mark.slow
