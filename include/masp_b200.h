@@ -42,6 +42,8 @@ extern "C" {
 #define MB200_ESTATE (-5)  /* mb200_init not called */
 #define MB200_ESCALAR (-6) /* a scalar is not canonical (>= r) */
 #define MB200_EVERIFY (-8) /* a proof failed the self-check (the reference returns Err(()) at sapling/prover.rs:148, :266) */
+#define MB200_EPARAMS (-9) /* parameter file: wrong size or BLAKE2b-512 digest (the reference panics: lib.rs:290-293, 359-388) */
+#define MB200_EIO (-10)    /* parameter file cannot be opened / read (the reference panics: lib.rs:316-318) */
 #define MB200_ESYNTH (-7)  /* witness generation failed (bellman SynthesisError: division by zero / unsatisfiable) */
 
 #define MB200_PROOF_BYTES 192 /* GROTH_PROOF_SIZE, masp_primitives/src/transaction/components.rs:14-15 */
@@ -67,6 +69,23 @@ int mb200_device_count(void);
  * per-window tables resident in HBM; it is immutable and may be shared. */
 int mb200_params_load(const uint8_t* bytes, size_t len, const uint8_t* a_aux_density,
                       const uint8_t* b_input_density, const uint8_t* b_aux_density, mb200_params** out);
+/* load_parameters / parse_parameters for one file (masp_proofs/src/lib.rs:278-325, 343-388): the size is
+ * checked against expected_bytes BEFORE anything is read (verify_file_size), Parameters::read(.., false)
+ * consumes the key, and the whole stream -- the MPC transcript behind the key included -- is BLAKE2b-512
+ * hashed and its hex digest compared with expected_blake2b_hex (verify_hash).  expected_bytes = 0 or an
+ * empty / NULL digest skips that check.  mb200_masp_params_spec returns the reference's constants
+ * (lib.rs:61-76) for kind = MB200_CIRCUIT_{SPEND,OUTPUT,CONVERT}.  Failures: MB200_EIO, MB200_EPARAMS,
+ * MB200_EPARSE where the reference panics. */
+int mb200_params_load_file(const char* path, uint64_t expected_bytes, const char* expected_blake2b_hex,
+                           const uint8_t* a_aux_density, const uint8_t* b_input_density, const uint8_t* b_aux_density,
+                           mb200_params** out);
+/* the same for bytes already in memory (LocalTxProver::from_bytes -> parse_parameters, prover.rs:120-136) */
+int mb200_params_load_verified(const uint8_t* bytes, size_t len, uint64_t expected_bytes, const char* expected_blake2b_hex,
+                               const uint8_t* a_aux_density, const uint8_t* b_input_density,
+                               const uint8_t* b_aux_density, mb200_params** out);
+int mb200_masp_params_spec(int kind, uint64_t* expected_bytes, char blake2b_hex[129], const char** file_name);
+/* BLAKE2b-512 of a byte string (host only; what `b2sum` prints) */
+int mb200_blake2b512(const uint8_t* bytes, size_t len, uint8_t out[64]);
 /* info[0..9] = n_inputs, n_aux, h_len, a_len, b_len, m, bytes consumed,
  * table bytes in HBM, window bits of the H+L table, window bits of the A table */
 int mb200_params_info(const mb200_params* p, uint64_t info[10]);

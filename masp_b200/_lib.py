@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmasp_b200.so")
 
 SYMBOLS = [
-    "mb200_init", "mb200_shutdown", "mb200_device_count", "mb200_params_load", "mb200_params_info", "mb200_params_free",
+    "mb200_init", "mb200_shutdown", "mb200_device_count", "mb200_params_load", "mb200_params_load_file", "mb200_params_load_verified", "mb200_masp_params_spec", "mb200_blake2b512", "mb200_params_info", "mb200_params_free",
     "mb200_params_synth_size", "mb200_params_synthesize", "mb200_synth_points", "mb200_prove_batch",
     "mb200_prove_batch_device", "mb200_prove_submit", "mb200_prove_wait", "mb200_msm_g1", "mb200_msm_g2", "mb200_g1_bases_upload", "mb200_dev_free",
     "mb200_msm_g1_partial", "mb200_g1_sum_partials", "mb200_msm_g1_partial_device", "mb200_g1_sum_partials_device",
@@ -42,6 +42,10 @@ def bind(path):
     L.mb200_shutdown.argtypes = []
     L.mb200_device_count.argtypes = []
     L.mb200_params_load.argtypes = [u8p, sz, u8p, u8p, u8p, c.POINTER(vp)]
+    L.mb200_params_load_file.argtypes = [u8p, u64, u8p, u8p, u8p, u8p, c.POINTER(vp)]
+    L.mb200_params_load_verified.argtypes = [u8p, sz, u64, u8p, u8p, u8p, u8p, c.POINTER(vp)]
+    L.mb200_masp_params_spec.argtypes = [c.c_int, c.POINTER(u64), vp, c.POINTER(c.c_char_p)]
+    L.mb200_blake2b512.argtypes = [vp, sz, vp]
     L.mb200_params_info.argtypes = [vp, c.POINTER(u64)]
     L.mb200_params_free.argtypes = [vp]
     L.mb200_params_free.restype = None

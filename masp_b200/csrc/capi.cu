@@ -3,11 +3,13 @@
 // every entry point needs mb200_init to have found a CUDA device.
 #include <algorithm>
 #include <array>
+#include <cstdio>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <thread>
 
+#include "host/blake2b.hpp"
 #include "host/circuit_obj.hpp"
 #include "prover.cuh"
 #include "synth.cuh"
@@ -728,20 +730,131 @@ int mb200_shutdown(void) {
     MB_API_END
 }
 
+static mb200_params* load_replicated(const uint8_t* bytes, size_t len, const uint8_t* a_aux_density,
+                                     const uint8_t* b_input_density, const uint8_t* b_aux_density);
+
 int mb200_params_load(const uint8_t* bytes, size_t len, const uint8_t* a_aux_density, const uint8_t* b_input_density,
                       const uint8_t* b_aux_density, mb200_params** out) {
     MB_API_BEGIN
     require_init();
     if (!out) fail(MB200_EINVAL, "null out pointer%s", "");
     *out = nullptr;
+    *out = load_replicated(bytes, len, a_aux_density, b_input_density, b_aux_density);
+    MB_API_END
+}
+
+// load_parameters / parse_parameters of the reference (masp_proofs/src/lib.rs:278-325, 343-388) for ONE
+// file: (1) the size must equal expected_bytes before anything is hashed; (2) Parameters::read(.., false)
+// consumes the key; (3) the WHOLE stream, transcript included, is BLAKE2b-512 hashed and the hex digest
+// compared.  The reference panics where this returns MB200_EPARAMS / MB200_EIO / MB200_EPARSE.
+static void check_stream(const uint8_t* bytes, size_t len, uint64_t expected_bytes, const char* expected_hex,
+                         const char* what) {
+    if (expected_bytes && len != expected_bytes)
+        fail(MB200_EPARAMS, "%s: parameter file size is not correct (%ld bytes)", what, (long)len);
+    if (expected_hex && *expected_hex) {
+        if (strlen(expected_hex) != 128) fail(MB200_EINVAL, "expected BLAKE2b-512 digest must be 128 hex digits%s", "");
+        char got[129];
+        mbh::blake2b512_hex(bytes, len, got);
+        for (int i = 0; i < 128; ++i) {
+            char e = expected_hex[i];
+            if (e >= 'A' && e <= 'F') e = (char)(e - 'A' + 'a');
+            if (e != got[i]) {
+                got[16] = 0;
+                fail(MB200_EPARAMS, "parameter file is not correct: BLAKE2b-512 = %s... over %ld bytes", got, (long)len);
+            }
+        }
+    }
+}
+static mb200_params* load_replicated(const uint8_t* bytes, size_t len, const uint8_t* a_aux_density,
+                                     const uint8_t* b_input_density, const uint8_t* b_aux_density) {
     std::unique_ptr<mb200_params, void (*)(mb200_params*)> p(new mb200_params(), params_destroy);
     p->rep.assign(g.devs.size(), nullptr);
     // replicate: every device ingests the bytes and expands its own window tables, in parallel
     for_devices(all_devices(), [&](Device& d) {
         p->rep[d.slot] = params_load(bytes, len, a_aux_density, b_input_density, b_aux_density, d.main);
     });
-    *out = p.release();
+    return p.release();
+}
+
+int mb200_params_load_verified(const uint8_t* bytes, size_t len, uint64_t expected_bytes, const char* expected_blake2b_hex,
+                               const uint8_t* a_aux_density, const uint8_t* b_input_density,
+                               const uint8_t* b_aux_density, mb200_params** out) {
+    MB_API_BEGIN
+    require_init();
+    if (!out || !bytes) fail(MB200_EINVAL, "null argument%s", "");
+    *out = nullptr;
+    if (expected_bytes && len != expected_bytes) check_stream(bytes, len, expected_bytes, nullptr, "stream");
+    mb200_params* p = load_replicated(bytes, len, a_aux_density, b_input_density, b_aux_density);
+    try {
+        check_stream(bytes, len, expected_bytes, expected_blake2b_hex, "stream");
+    } catch (...) {
+        params_destroy(p);
+        throw;
+    }
+    *out = p;
     MB_API_END
+}
+
+int mb200_params_load_file(const char* path, uint64_t expected_bytes, const char* expected_blake2b_hex,
+                           const uint8_t* a_aux_density, const uint8_t* b_input_density, const uint8_t* b_aux_density,
+                           mb200_params** out) {
+    MB_API_BEGIN
+    require_init();
+    if (!out || !path) fail(MB200_EINVAL, "null argument%s", "");
+    *out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) fail(MB200_EIO, "couldn't load parameters file %s", path);
+    std::vector<uint8_t> buf;
+    try {
+        // verify_file_size first (lib.rs:284-311): nothing is read or hashed when the size is off
+        if (fseek(f, 0, SEEK_END) != 0) fail(MB200_EIO, "cannot seek in %s", path);
+        long size = ftell(f);
+        if (size < 0) fail(MB200_EIO, "cannot size %s", path);
+        if (expected_bytes && (uint64_t)size != expected_bytes)
+            fail(MB200_EPARAMS, "%s: parameter file size is not correct (%ld bytes)", path, size);
+        rewind(f);
+        buf.resize((size_t)size);
+        if (size && fread(buf.data(), 1, (size_t)size, f) != (size_t)size) fail(MB200_EIO, "short read from %s", path);
+    } catch (...) {
+        fclose(f);
+        throw;
+    }
+    fclose(f);
+    mb200_params* p = load_replicated(buf.data(), buf.size(), a_aux_density, b_input_density, b_aux_density);
+    try {
+        check_stream(buf.data(), buf.size(), expected_bytes, expected_blake2b_hex, path);
+    } catch (...) {
+        params_destroy(p);
+        throw;
+    }
+    *out = p;
+    MB_API_END
+}
+
+int mb200_masp_params_spec(int kind, uint64_t* expected_bytes, char blake2b_hex[129], const char** file_name) {
+    // masp_proofs/src/lib.rs:61-76
+    static const struct {
+        const char* name;
+        const char* hash;
+        uint64_t bytes;
+    } spec[3] = {
+        {"masp-spend.params", "196e7c717f25e16653431559ce2c8816e750a4490f98696e3c031efca37e25e0647182b7b013660806db11eb2b1e365fb2d6a0f24dbbd9a4a8314fef10a7cba2", 49848572ull},
+        {"masp-output.params", "eafc3b1746cccc8b9eed2b69395692c5892f6aca83552a07dceb2dcbaa64dcd0e22434260b3aa3b049b633a08b008988cbe0d31effc77e2bc09bfab690a23724", 16398620ull},
+        {"masp-convert.params", "dc4aaf3c3ce056ab448b6c4a7f43c1d68502c2902ea89ab8769b1524a2e8ace9a5369621a73ee1daa52aec826907a19974a37874391cf8f11bbe0b0420de1ab7", 22570940ull},
+    };
+    if (kind < 0 || kind > 2) return MB200_EINVAL;
+    if (expected_bytes) *expected_bytes = spec[kind].bytes;
+    if (blake2b_hex) memcpy(blake2b_hex, spec[kind].hash, 129);
+    if (file_name) *file_name = spec[kind].name;
+    return MB200_OK;
+}
+
+int mb200_blake2b512(const uint8_t* bytes, size_t len, uint8_t out[64]) {
+    if ((len && !bytes) || !out) return MB200_EINVAL;
+    mbh::Blake2b b;
+    b.update(bytes, len);
+    b.finish(out);
+    return MB200_OK;
 }
 
 int mb200_params_info(const mb200_params* p, uint64_t info[10]) {
@@ -1491,6 +1604,8 @@ const char* mb200_strerror(int code) {
         case MB200_ESCALAR: return "scalar is not canonical";
         case MB200_ESYNTH: return "witness generation failed";
         case MB200_EVERIFY: return "proof does not verify";
+        case MB200_EPARAMS: return "parameter file size or BLAKE2b digest is not the expected one";
+        case MB200_EIO: return "cannot read the parameter file";
         default: return "unknown error";
     }
 }

@@ -135,6 +135,33 @@ class Parameters:
         check(_lib.lib().mb200_params_info(h, info))
         return cls(h, [int(x) for x in info])
 
+    @classmethod
+    def read_verified(cls, buf, expected_bytes, expected_hash, densities=None):
+        """One stream of parse_parameters (masp_proofs/src/lib.rs:343-388) behind the C ABI:
+        Parameters::read(.., false), then BLAKE2b-512 over the whole stream (transcript included)."""
+        _ensure_init()
+        a_d, bi_d, ba_d = densities if densities is not None else (None, None, None)
+        h = ctypes.c_void_p()
+        buf = bytes(buf) if not isinstance(buf, bytes) else buf
+        check(_lib.lib().mb200_params_load_verified(buf, len(buf), int(expected_bytes or 0),
+                                                    (expected_hash or "").encode(), a_d, bi_d, ba_d, ctypes.byref(h)))
+        info = (ctypes.c_uint64 * 10)()
+        check(_lib.lib().mb200_params_info(h, info))
+        return cls(h, [int(x) for x in info])
+
+    @classmethod
+    def read_file(cls, path, expected_bytes, expected_hash, densities=None):
+        """One file of load_parameters (lib.rs:278-325): size check before anything is read,
+        then as read_verified.  The file never passes through Python."""
+        _ensure_init()
+        a_d, bi_d, ba_d = densities if densities is not None else (None, None, None)
+        h = ctypes.c_void_p()
+        check(_lib.lib().mb200_params_load_file(os.fsencode(path), int(expected_bytes or 0), (expected_hash or "").encode(),
+                                                a_d, bi_d, ba_d, ctypes.byref(h)))
+        info = (ctypes.c_uint64 * 10)()
+        check(_lib.lib().mb200_params_info(h, info))
+        return cls(h, [int(x) for x in info])
+
     def bind_circuit(self, circuit):
         """Attach a recorded circuit (masp_b200.circuits.Circuit): its matrices go to
         the device once, after which create_proof_batch_from_witness needs only
@@ -330,12 +357,6 @@ class ParameterError(Exception):
     """The reference panics here (masp_proofs/src/lib.rs:290-293, 316-318, 359-388)."""
 
 
-def _verify_file_size(path, expected, name):
-    size = os.path.getsize(path)
-    if size != expected:
-        raise ParameterError("%s parameter file size is not correct: %d, expected %d" % (name, size, expected))
-
-
 def masp_circuits():
     """The three recorded circuits (masp_b200.circuits.Circuit), built once per process."""
     global _circuits
@@ -346,6 +367,30 @@ def masp_circuits():
 
 
 _circuits = None
+_SPEC = {"spend": (MASP_SPEND_BYTES, MASP_SPEND_HASH), "output": (MASP_OUTPUT_BYTES, MASP_OUTPUT_HASH),
+         "convert": (MASP_CONVERT_BYTES, MASP_CONVERT_HASH)}
+
+
+def _load_three(loader, sources, densities, verify):
+    """Shared tail of load_parameters / parse_parameters: the size and BLAKE2b-512 semantics live in
+    the library (mb200_params_load_file / _verified); a failed check is the reference's panic."""
+    bind = densities is None
+    if bind:
+        circs = masp_circuits()
+        densities = {k: c.densities() for k, c in circs.items()}
+    dens = densities or {}
+    out = {}
+    for name in ("spend", "output", "convert"):
+        size, digest = _SPEC[name] if verify else (0, "")
+        try:
+            out[name] = loader(sources[name], size, digest, dens.get(name))
+        except Mb200Error as e:
+            if e.code in (-9, -10):
+                raise ParameterError("MASP %s parameter file is not correct: %s" % (name, e)) from e
+            raise
+        if bind:
+            out[name].bind_circuit(circs[name])
+    return out
 
 
 def parse_parameters(spend_bytes, output_bytes, convert_bytes, densities=None, verify_hashes=True):
@@ -356,32 +401,21 @@ def parse_parameters(spend_bytes, output_bytes, convert_bytes, densities=None, v
     densities=None (the reference's signature has no such argument): the
     bitmaps come from the library's own recorded circuits, which are then bound
     to the keys so that the *_proof methods accept circuit instances."""
-    bind = densities is None
-    if bind:
-        circs = masp_circuits()
-        densities = {k: c.densities() for k, c in circs.items()}
-    dens = densities or {}
-    out = {}
-    for name, buf, want in (("spend", spend_bytes, MASP_SPEND_HASH), ("output", output_bytes, MASP_OUTPUT_HASH),
-                            ("convert", convert_bytes, MASP_CONVERT_HASH)):
-        if verify_hashes:
-            got = hashlib.blake2b(buf, digest_size=64).hexdigest()
-            if got != want:
-                raise ParameterError("MASP %s parameter file is not correct (BLAKE2b %s...)" % (name, got[:16]))
-        out[name] = Parameters.read(buf, dens.get(name))
-        if bind:
-            out[name].bind_circuit(circs[name])
-    return out
+    src = {"spend": spend_bytes, "output": output_bytes, "convert": convert_bytes}
+    # from bytes the reference checks the digest only (no file size to look at)
+    loader = lambda buf, size, digest, d: Parameters.read_verified(buf, 0, digest, d)
+    return _load_three(loader, src, densities, verify_hashes)
 
 
 def load_parameters(spend_path, output_path, convert_path, densities=None, verify=True):
-    """load_parameters (masp_proofs/src/lib.rs:278-325)."""
-    if verify:
-        _verify_file_size(spend_path, MASP_SPEND_BYTES, "masp spend")
-        _verify_file_size(output_path, MASP_OUTPUT_BYTES, "masp output")
-        _verify_file_size(convert_path, MASP_CONVERT_BYTES, "masp convert")
-    rd = lambda p: open(p, "rb").read()
-    return parse_parameters(rd(spend_path), rd(output_path), rd(convert_path), densities, verify_hashes=verify)
+    """load_parameters (masp_proofs/src/lib.rs:278-325): file sizes first, then parse_parameters."""
+    src = {"spend": spend_path, "output": output_path, "convert": convert_path}
+    if verify:   # all three sizes are checked before any file is opened (lib.rs:284-311)
+        for name in ("spend", "output", "convert"):
+            size = os.path.getsize(src[name])
+            if size != _SPEC[name][0]:
+                raise ParameterError("masp %s parameter file size is not correct: %d, expected %d" % (name, size, _SPEC[name][0]))
+    return _load_three(Parameters.read_file, src, densities, verify)
 
 
 def default_params_folder():
@@ -423,27 +457,35 @@ class LocalTxProver:
     @staticmethod
     def _prove(instance, params, rng, check):
         if isinstance(instance, ProvingAssignment):
-            return create_random_proof(instance, params, rng)
-        circ = getattr(params, "circuit", None)
-        if circ is None:
-            raise ValueError("these parameters have no circuit bound; pass a ProvingAssignment")
-        inputs, aux = circ.synthesize([instance])
-        if check:  # verify_proof right after proving, as sapling/prover.rs:148 and :266 do
-            set_option("verify", 1)
-        try:
-            return create_proof_batch_from_witness(params, inputs, aux, [rng()], [rng()])[0]
-        finally:
-            if check:
-                set_option("verify", 0)
+            proof = create_random_proof(instance, params, rng)
+            inputs = instance.input_assignment
+        else:
+            circ = getattr(params, "circuit", None)
+            if circ is None:
+                raise ValueError("these parameters have no circuit bound; pass a ProvingAssignment")
+            inputs, aux = circ.synthesize([instance])
+            inputs = bytes(inputs)
+            proof = create_proof_batch_from_witness(params, inputs, aux, [rng()], [rng()])[0]
+        if check:
+            # verify_proof right after proving, as sapling/prover.rs:148 and :266 do -- an explicit call on
+            # the returned bytes, not the library-wide "verify" option (which belongs to whoever set it and
+            # would race with batches other threads have in flight); failure is the reference's Err(())
+            xs = [int.from_bytes(inputs[32 * i:32 * (i + 1)], "little") for i in range(1, params.n_inputs)]
+            if not verify_proofs(params, [proof], [xs])[0]:
+                raise Mb200Error(-8, "proof does not satisfy the verification equation")
+        return proof
 
-    def spend_proof(self, instance, rng=_os_rng_scalar):
-        return self._prove(instance, self.spend_params, rng, True)
+    # self_check: the reference always verifies Spend and Convert proofs before returning them
+    # (sapling/prover.rs:148, :266); False is for keys that are not a valid CRS (benchmarks on
+    # synthetic parameters, like the reference's generate_random_parameters benches)
+    def spend_proof(self, instance, rng=_os_rng_scalar, self_check=True):
+        return self._prove(instance, self.spend_params, rng, self_check)
 
     def output_proof(self, instance, rng=_os_rng_scalar):
         return self._prove(instance, self.output_params, rng, False)   # the reference does not self-check outputs
 
-    def convert_proof(self, instance, rng=_os_rng_scalar):
-        return self._prove(instance, self.convert_params, rng, True)
+    def convert_proof(self, instance, rng=_os_rng_scalar, self_check=True):
+        return self._prove(instance, self.convert_params, rng, self_check)
 
     def prove_bundle(self, spends=(), converts=(), outputs=(), rng=_os_rng_scalar):
         """All descriptions of a transaction in one launch per circuit (the

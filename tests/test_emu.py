@@ -88,8 +88,43 @@ def test_local_tx_prover_surface(emu, oracle):
     want = oracle_proofs(oracle, kb, sh, sh.densities(), ws)
     assert [got[0][0], got[1][0], got[2][0]] == want
     # create_random_proof draws r, s itself: two calls must differ, both must be 192 bytes
-    p1, p2 = prover.spend_proof(spends[0]), prover.spend_proof(spends[0])
+    p1, p2 = prover.spend_proof(spends[0], self_check=False), prover.spend_proof(spends[0], self_check=False)
     assert len(p1) == len(p2) == 192 and p1 != p2
+    # with the self-check on (the reference's behaviour) an unsatisfied witness is Err(()), not a proof
+    with pytest.raises(emu.Mb200Error):
+        prover.spend_proof(spends[0])
+    # load_parameters semantics behind the C ABI (masp_proofs/src/lib.rs:278-325, 343-388): size first, then
+    # Parameters::read, then BLAKE2b-512 over the whole stream, transcript included
+    import hashlib
+    import os
+    import tempfile
+    blob = kb + tail
+    digest = hashlib.blake2b(blob, digest_size=64).hexdigest()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "masp-test.params")
+        open(path, "wb").write(blob)
+        P = emu.Parameters.read_file(path, len(blob), digest, sh.densities())
+        assert P.consumed == len(kb) and (P.n_inputs, P.n_aux) == (sh.n_inputs, sh.n_aux)
+        for size, dg, code in ((len(blob) + 1, digest, -9), (len(blob), digest[:-1] + ("0" if digest[-1] != "0" else "1"), -9),
+                               (0, "", None)):
+            if code is None:
+                emu.Parameters.read_file(path, size, dg, sh.densities())
+                continue
+            with pytest.raises(emu.Mb200Error) as e:
+                emu.Parameters.read_file(path, size, dg, sh.densities())
+            assert e.value.code == code
+        with pytest.raises(emu.Mb200Error) as e:
+            emu.Parameters.read_file(os.path.join(d, "absent.params"), 0, "", sh.densities())
+        assert e.value.code == -10
+    assert emu.Parameters.read_verified(blob, len(blob), digest.upper(), sh.densities()).consumed == len(kb)
+    with pytest.raises(emu.Mb200Error):
+        emu.Parameters.read_verified(blob[:-1], len(blob) - 1, digest, sh.densities())
+    # the library's BLAKE2b against hashlib on awkward lengths (block boundaries)
+    import ctypes
+    for n in (0, 1, 127, 128, 129, 255, 256, 257, 1000):
+        out = ctypes.create_string_buffer(64)
+        assert emu._lib.lib().mb200_blake2b512(blob[:n], n, ctypes.cast(out, ctypes.c_void_p)) == 0
+        assert out.raw == hashlib.blake2b(blob[:n], digest_size=64).digest(), n
 
 
 def test_msm_special_bases(emu, oracle):
@@ -123,6 +158,7 @@ def test_ntt_shared_memory_form(emu, oracle):
     for any rows) -- and it really is two launches where the pass form needs four to six."""
     for log_n in (11, 12, 16, 17):
         v = ib(rand_scalars(1 << log_n, log_n, "uniform"))
+        emu.ntt(v, log_n)     # builds the domain tables of this size (their launches are not the transform's)
         for inv in (False, True):
             for cos in (False, True):
                 l0 = emu.get_counter("launches")
