@@ -186,7 +186,7 @@ def run_queue(pv, torch, items, in_flight):
         pv.prove_wait(tickets.pop(0))
 
 
-def circuit_path(pv, key, shape, n, rounds, seed=20261017, torch=None):
+def circuit_path(pv, key, shape, n, rounds, seed=20261017, torch=None, threads=0, sync=None):
     """The drop-in call a TxProver makes, measured: real Spend witnesses ->
     product-side witness generation on the host cores (mb200_circuit_synthesize)
     -> only inputs + aux cross PCIe -> rows on the device (r1cs_eval) -> proof.
@@ -229,7 +229,7 @@ def circuit_path(pv, key, shape, n, rounds, seed=20261017, torch=None):
     ring = [(pinned(n * circ.n_inputs * 32), pinned(n * circ.n_aux * 32)) for _ in range(6)]
     # each stage alone
     t0 = time.perf_counter()
-    inputs, aux = circ.synthesize(packed[0], out=ring[0])
+    inputs, aux = circ.synthesize(packed[0], out=ring[0], threads=threads)
     t_synth = time.perf_counter() - t0
     pv.prove_wait(pv.prove_submit_witness(params, n, inputs, aux, r_b, s_b, outs[0]))  # warm-up
     t0 = time.perf_counter()
@@ -246,7 +246,9 @@ def circuit_path(pv, key, shape, n, rounds, seed=20261017, torch=None):
 
         def prod():
             for k in range(rounds):
-                qq.put(circ.synthesize(packed[k], out=fr.get()))
+                qq.put(circ.synthesize(packed[k], out=fr.get(), threads=threads))
+        if sync:
+            sync()
         t1 = time.perf_counter()
         thr = threading.Thread(target=prod)
         thr.start()
@@ -262,22 +264,23 @@ def circuit_path(pv, key, shape, n, rounds, seed=20261017, torch=None):
             pv.prove_wait(tk.pop(0))
             fr.put(kp.pop(0))
         thr.join()
-        return rounds * n / (time.perf_counter() - t1)
-    plain = pipelined(2)
+        dt = time.perf_counter() - t1
+        return rounds * n / dt, dt
+    plain, t_plain = pipelined(2)
     # the reference's spend_proof also runs verify_proof on the fresh proof (sapling/prover.rs:148):
     # same pipeline with the device self-check on (audit mode: this key is not a valid CRS, so the
     # verdicts are 'fail' by construction; the kernel and its cost are the same)
     pv.set_option("verify", 2)
     try:
-        with_check = pipelined(4)
+        with_check, _ = pipelined(4)
     finally:
         pv.set_option("verify", 0)
     return {
         "what": "real Spend witnesses through mb200_circuit_synthesize + mb200_prove_batch_witness "
                 "(what TxProver::spend_proof does per description, batched)",
         "proofs_per_s_pipelined": plain, "proofs_per_s_pipelined_with_self_check": with_check,
-        "batch": n, "rounds": rounds,
-        "host_witness_per_s": n / t_synth, "host_threads": os.cpu_count(),
+        "seconds_pipelined": t_plain, "batch": n, "rounds": rounds,
+        "host_witness_per_s": n / t_synth, "host_threads": threads or os.cpu_count(),
         "device_proofs_per_s": n / t_prove,
         "h2d_bytes_per_proof": 32 * (circ.n_aux + circ.n_inputs + 2),
         "h2d_bytes_per_proof_with_rows": 32 * (3 * circ.rows + circ.n_aux + circ.n_inputs + 2),
@@ -369,30 +372,34 @@ def msm_sweep(pv, torch, dist, rank, world, ndev, sizes, kinds, reps, check):
             gathered = torch.zeros(world * 192, dtype=torch.uint8, device="cuda") if world > 1 else None
             mine = torch.zeros(192, dtype=torch.uint8, device="cuda")
             times, acc_us, result = [], [], None
-            for rep in range(reps + 1):
-                pv.set_option("profile", 1)
+
+            def one_call():
+                if ndev > 1:
+                    return gb.msm(sc)
+                gb.msm_partial_into(sc, mine)
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered, mine)   # NCCL, device buffers: K6's exchange
+                    return pv.g1_sum_partials_device(gathered, world)
+                return pv.g1_sum_partials_device(mine, 1)
+            for rep in range(reps + 2):
+                profiled = rep == reps + 1      # the last call times the accumulation kernels (event syncs inside)
+                if profiled:
+                    pv.set_option("profile", 1)
                 torch.cuda.synchronize()
                 if world > 1:
                     dist.barrier()
                 t0 = time.perf_counter()
-                if ndev > 1:
-                    result = gb.msm(sc)
-                else:
-                    gb.msm_partial_into(sc, mine)
-                    if world > 1:
-                        dist.all_gather_into_tensor(gathered, mine)   # NCCL, device buffers: K6's exchange
-                        result = pv.g1_sum_partials_device(gathered, world)
-                    else:
-                        result = pv.g1_sum_partials_device(mine, 1)
+                result = one_call()
                 dt = time.perf_counter() - t0
                 if world > 1:
                     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
                     dist.all_reduce(t, op=dist.ReduceOp.MAX)
                     dt = float(t.item())
-                if rep:
-                    times.append(dt)
+                if profiled:
                     acc_us.append(pv.get_counter("acc_us"))
-                pv.set_option("profile", 0)
+                    pv.set_option("profile", 0)
+                elif rep:                       # the first call is warm-up
+                    times.append(dt)
             if rank == 0:
                 ok = None
                 if check:
@@ -607,6 +614,27 @@ def main():
     if not args.no_msm_sweep and shape.name == "spend":
         sweep = msm_sweep(pv, torch, dist, rank, world, ndev, args.msm_sizes, ["U", "W"], 2, check=True)
 
+    # the drop-in call with REAL Spend witnesses, at any N: every rank generates its own witnesses on its
+    # share of the host threads (one process: all of them) and proves them on its GPU(s)
+    cpath = None
+    if not args.no_circuit_path and shape.name == "spend":
+        try:
+            threads = max(1, (os.cpu_count() or 1) // world)
+            cpath = circuit_path(pv, key, shape, args.circuit_batch * ndev, args.circuit_rounds, torch=torch,
+                                 threads=threads, sync=barrier)
+            if world > 1:
+                t = max_over_ranks(cpath["seconds_pipelined"])
+                cpath["proofs_per_s_pipelined_per_rank"] = cpath["proofs_per_s_pipelined"]
+                cpath["proofs_per_s_pipelined"] = world * cpath["batch"] * cpath["rounds"] / t
+                hw = torch.tensor([cpath["host_witness_per_s"]], dtype=torch.float64, device="cuda")
+                dist.all_reduce(hw)
+                cpath["host_witness_per_s"] = float(hw.item())
+                cpath["host_threads_per_rank"] = threads
+        except Exception as e:  # reported, never silently dropped
+            cpath = {"error": repr(e)}
+            if world > 1:
+                raise
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -674,11 +702,10 @@ def main():
     if sweep is not None:
         line.setdefault("configs", {})["msm_sweep"] = sweep
 
-    if n_gpus == 1 and not args.no_circuit_path:
-        try:
-            line["circuit_path"] = circuit_path(pv, key, shape, args.circuit_batch, args.circuit_rounds, torch=torch)
-        except Exception as e:  # reported, never silently dropped
-            line["circuit_path"] = {"error": repr(e)}
+    if cpath is not None:
+        cpath["n_gpus"] = n_gpus
+        cpath["vs_synthetic_rows_e2e"] = (cpath["proofs_per_s_pipelined"] / e2e_value) if "proofs_per_s_pipelined" in cpath else None
+        line["circuit_path"] = cpath
 
     if not args.no_cpu_baseline:
         from oracle import c_oracle as co

@@ -258,7 +258,8 @@ int mb200_fr_mul(const uint8_t* a, const uint8_t* b, size_t n, uint8_t* out);
 int mb200_fr_mul_device(const void* a, const void* b, size_t n, void* out);
 
 /* knobs: "chunk" proofs per in-flight chunk; "streams" in-flight chunks per device; "verify" 0/1/2 self-check;
- * "profile" 0/1 event timing of the accumulation kernels (synchronises: measurement only) */
+ * "profile" 0/1 event timing of the accumulation kernels (synchronises: measurement only);
+ * "msm_slab" scalars per slab of a standalone MSM (default 2^22: slab k+1 uploads while slab k is reduced) */
 int mb200_set_option(const char* name, long value);
 /* counters: "launches" (kernels launched so far), "acc_launches",
  * "acc_us" (device time of the bucket-accumulation kernels, microseconds;

@@ -43,6 +43,14 @@ struct Device {
     MsmScratch msm;
     std::vector<TicketRes*> res_free;
     DevBuf peer_parts;  // slot 0 only: where the other devices' MSM partials land (K6)
+    // standalone MSM: scalars arrive in slabs through two buffers, uploaded on `copy` while the
+    // previous slab is being sorted and accumulated on `main`.  All of it persists across calls:
+    // cudaMalloc / cudaFree per call cost more than a 2^16 MSM itself.
+    cudaStream_t copy = 0;
+    DevBuf slab[2], msm_flag, msm_enc;
+#ifndef MB200_EMU
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+#endif
 };
 struct State {
     bool inited = false;
@@ -53,6 +61,7 @@ struct State {
                      // 2 = check and only count the failures (counter "verify_failed"; for measuring the cost)
     unsigned long long verify_failed = 0, verified = 0;
     size_t next_dev = 0;  // small batches rotate over the devices
+    size_t msm_slab = (size_t)1 << 22;  // standalone MSM: scalars per upload / sort / accumulate slab (option "msm_slab")
     std::mutex mu;
     double last_batch_ms = 0;  // device time of the last prove call (CUDA events on the chunk streams, max over devices)
 };
@@ -180,7 +189,10 @@ static uint32_t standalone_window(size_t n) {
     return env_u32("MB200_C_MSM", best);
 }
 
-// One MSM over device-resident bases on device `d`; scalars from host memory.  out_dev: one XYZZ on `d`.
+// One MSM over device-resident bases on device `d`; scalars from host memory (pinned memory makes
+// the uploads asynchronous).  out_dev: one XYZZ on `d`, complete when this returns.
+// The scalars are cut into slabs of MSM_SLAB: slab k+1 crosses PCIe while slab k is sorted and
+// accumulated into one shared set of buckets; the bucket reduction runs once, after the last slab.
 template <class F>
 static void msm_on_device_bases(Device& d, const Affine<F>* bases, const uint8_t* scalars_host, size_t n, XYZZ<F>* out_dev) {
     if (n == 0) {
@@ -189,17 +201,51 @@ static void msm_on_device_bases(Device& d, const Affine<F>* bases, const uint8_t
         return;
     }
     if (n >= (1ull << 31)) fail(MB200_EINVAL, "MSM of %s%ld bases is too large", "", (long)n);
-    DevBuf sel(n * 4), pool(n * 32), flag(4);
-    IotaArgs ia{n, sel.as<uint32_t>()};
-    launch_iota_kernel(ia, d.main);
-    copy_h2d(pool.p, scalars_host, n * 32, d.main);
-    dev_memset(flag.p, 0, 4, d.main);
-    ValidateArgs va{n, pool.as<Fr>(), n, n, flag.as<uint32_t>()};
-    launch_validate_scalars(va, d.main);
-    MsmClass k = msm_make_class(bases, sel.as<uint32_t>(), (uint32_t)n, standalone_window(n), false);
-    msm_run<F>(k, 1, pool.as<uint32_t>(), n, out_dev, d.msm, d.main);
+    const size_t nslab = (n + g.msm_slab - 1) / g.msm_slab;
+    const size_t per = (n + nslab - 1) / nslab;  // equal slabs, each <= msm_slab
+    for (int b = 0; b < (nslab > 1 ? 2 : 1); ++b) d.slab[b].ensure(per * 32);
+    d.msm_flag.ensure(4);
+    dev_memset(d.msm_flag.p, 0, 4, d.main);
+    const uint32_t c = standalone_window(n);
+    uint32_t n_ones = (uint32_t)std::min<size_t>(256, std::max<size_t>(1, per / 256));
+    auto upload = [&](size_t k) {
+        const size_t lo = k * per, cnt = std::min(per, n - lo);
+        const int b = (int)(k & 1);
+#ifndef MB200_EMU
+        if (k >= 2) MB_CUDA(cudaStreamWaitEvent(d.copy, d.ev_free[b], 0));   // slab k-2 has been consumed
+        else if (k == 0) {
+            MB_CUDA(cudaEventRecord(d.ev_free[0], d.main));                  // order after earlier work on main
+            MB_CUDA(cudaStreamWaitEvent(d.copy, d.ev_free[0], 0));
+        }
+#endif
+        cudaStream_t cs = d.copy;
+        copy_h2d(d.slab[b].p, scalars_host + lo * 32, cnt * 32, cs);
+#ifndef MB200_EMU
+        MB_CUDA(cudaEventRecord(d.ev_up[b], cs));
+#endif
+    };
+    upload(0);
+    MsmClass last;
+    for (size_t k = 0; k < nslab; ++k) {
+        const size_t lo = k * per, cnt = std::min(per, n - lo);
+        const int b = (int)(k & 1);
+        if (k + 1 < nslab) upload(k + 1);
+#ifndef MB200_EMU
+        MB_CUDA(cudaStreamWaitEvent(d.main, d.ev_up[b], 0));
+#endif
+        ValidateArgs va{cnt, d.slab[b].as<Fr>(), cnt, cnt, d.msm_flag.as<uint32_t>()};
+        launch_validate_scalars(va, d.main);
+        // every slab sorts and accumulates into the SAME bucket sets (same c, same layout); the bucket
+        // reduction and the Horner step over the windows run once, after the last slab
+        last = msm_make_class(bases + lo, nullptr, (uint32_t)cnt, c, false, n_ones);
+        msm_accumulate_buckets<F>(last, 1, d.slab[b].as<uint32_t>(), cnt, d.msm, d.main, k > 0);
+#ifndef MB200_EMU
+        MB_CUDA(cudaEventRecord(d.ev_free[b], d.main));
+#endif
+    }
+    msm_reduce_buckets<F>(last, 1, out_dev, d.msm, d.main);
     uint32_t bad = 0;
-    copy_d2h(&bad, flag.p, 4, d.main);
+    copy_d2h(&bad, d.msm_flag.p, 4, d.main);
     stream_sync(d.main);
     if (bad) fail(MB200_ESCALAR, "a scalar is not canonical (>= r)%s", "");
 }
@@ -672,6 +718,11 @@ int mb200_init(const int* device_ids, int n_devices) {
             use(d);
 #ifndef MB200_EMU
             MB_CUDA(cudaStreamCreateWithFlags(&d.main, cudaStreamNonBlocking));
+            MB_CUDA(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
+            for (int b = 0; b < 2; ++b) {
+                MB_CUDA(cudaEventCreateWithFlags(&d.ev_up[b], cudaEventDisableTiming));
+                MB_CUDA(cudaEventCreateWithFlags(&d.ev_free[b], cudaEventDisableTiming));
+            }
             for (auto& v : d.vstream) MB_CUDA(cudaStreamCreateWithFlags(&v, cudaStreamNonBlocking));
 #endif
             set_ctx_count(d, g.n_streams);
@@ -720,7 +771,15 @@ int mb200_shutdown(void) {
         d.res_free.clear();
         d.msm = MsmScratch();
         d.peer_parts.release();
+        for (auto& b : d.slab) b.release();
+        d.msm_flag.release();
+        d.msm_enc.release();
 #ifndef MB200_EMU
+        cudaStreamDestroy(d.copy);
+        for (int b = 0; b < 2; ++b) {
+            cudaEventDestroy(d.ev_up[b]);
+            cudaEventDestroy(d.ev_free[b]);
+        }
         cudaStreamDestroy(d.main);
         for (auto& v : d.vstream) cudaStreamDestroy(v);
 #endif
@@ -1270,10 +1329,10 @@ int mb200_g1_sum_partials_device(const void* dev_partials, size_t count, uint8_t
     MB_API_BEGIN
     Device& d = dev0();
     if ((count && !dev_partials) || !out) fail(MB200_EINVAL, "null buffer%s", "");
-    DevBuf enc(96);
-    SumPartialsArgs sa{1, (const G1XYZZ*)dev_partials, count, enc.as<uint8_t>()};
+    d.msm_enc.ensure(96);
+    SumPartialsArgs sa{1, (const G1XYZZ*)dev_partials, count, d.msm_enc.as<uint8_t>()};
     launch_sum_partials(sa, d.main);
-    copy_d2h(out, enc.p, 96, d.main);
+    copy_d2h(out, d.msm_enc.p, 96, d.main);
     stream_sync(d.main);
     MB_API_END
 }
@@ -1367,10 +1426,10 @@ int mb200_msm_g1_bases(const mb200_g1_bases* b, const uint8_t* scalars, size_t n
 #endif
     });
     use(d0);
-    DevBuf enc(96);
-    SumPartialsArgs sa{1, gathered, nd, enc.as<uint8_t>()};
+    d0.msm_enc.ensure(96);
+    SumPartialsArgs sa{1, gathered, nd, d0.msm_enc.as<uint8_t>()};
     launch_sum_partials(sa, d0.main);
-    copy_d2h(out, enc.p, 96, d0.main);
+    copy_d2h(out, d0.msm_enc.p, 96, d0.main);
     stream_sync(d0.main);
     MB_API_END
 }
@@ -1462,6 +1521,9 @@ int mb200_set_option(const char* name, long value) {
             set_ctx_count(*d, (size_t)value);
         }
         use(*g.devs[0]);
+    } else if (!strcmp(name, "msm_slab")) {
+        if (value < 1 || value > (1l << 26)) fail(MB200_EINVAL, "msm_slab out of range%s (%ld)", "", value);
+        g.msm_slab = (size_t)value;
     } else if (!strcmp(name, "verify")) {
         if (value < 0 || value > 2) fail(MB200_EINVAL, "verify out of range%s (%ld)", "", value);
         g.verify = (int)value;

@@ -28,7 +28,7 @@ namespace mb {
 
 struct MsmClass {
     const void* table;     // Affine<F>[ (precomp ? nwin : 1) * n_bases ]
-    const uint32_t* sel;   // n_bases: index of each base's scalar inside an instance's scalar pool
+    const uint32_t* sel;   // n_bases: index of each base's scalar inside an instance's scalar pool (nullptr: base k <-> scalar k)
     uint32_t n_bases;
     uint32_t c;            // window bits
     uint32_t nwin;         // windows: nwin * c >= 256
@@ -42,7 +42,8 @@ struct MsmClass {
 
 inline uint32_t msm_nwin(uint32_t c) { return (256 + c - 1) / c; }
 
-inline MsmClass msm_make_class(const void* table, const uint32_t* sel, uint32_t n_bases, uint32_t c, bool precomp) {
+inline MsmClass msm_make_class(const void* table, const uint32_t* sel, uint32_t n_bases, uint32_t c, bool precomp,
+                               uint32_t n_ones = 0) {
     MsmClass k;
     k.table = table;
     k.sel = sel;
@@ -52,7 +53,7 @@ inline MsmClass msm_make_class(const void* table, const uint32_t* sel, uint32_t 
     k.nb = 1u << (c - 1);
     k.precomp = precomp ? 1 : 0;
     k.nsets = precomp ? 1 : k.nwin;
-    uint32_t ones = n_bases / 256;
+    uint32_t ones = n_ones ? n_ones : n_bases / 256;  // n_ones given: slabs of one MSM share a bucket layout
     if (ones < 1) ones = 1;
     if (ones > 256) ones = 256;
     k.n_ones = ones;
@@ -89,7 +90,7 @@ MB_HD void digit_body(const DigitArgs& a, size_t tid) {
     const MsmClass& k = a.k;
     size_t inst = tid / k.n_bases;
     uint32_t base = (uint32_t)(tid - inst * k.n_bases);
-    const uint32_t* sp = a.pool + (inst * a.pool_stride + k.sel[base]) * 8;
+    const uint32_t* sp = a.pool + (inst * a.pool_stride + (k.sel ? k.sel[base] : base)) * 8;
     uint32_t s[8];
     uint32_t any_hi = 0;
     MB_UNROLL
@@ -285,22 +286,64 @@ MB_K_MSM_G2(msm_accumulate_g2, AccArgs<Fp2>, acc_g2_body, 64)
 // (its accumulator in shared memory -- 168 registers, 12 warps per SM instead of 255 and 8 --
 // measured 457 against 492 proofs/s: the ~800 LDS / STS per addition cost more than the spills.)
 
-// bucket sum = sum of its segments' partial sums (one for almost every bucket)
+// bucket sum = sum of its segments' partial sums.  Almost every bucket has ONE segment; a heavy
+// bucket (the partly filled top window of a 255-bit scalar puts n / 8 entries into each of eight
+// buckets; real witnesses repeat small values) has thousands, and one thread adding them serially
+// was the cliff of the 2^24 MSM: 420 of 650 ms in this step (profiles/r02_launches_msm24.csv).  So the
+// partial sums of a bucket are folded as an in-place tree of fan-in COMBINE_F: in round r the thread
+// of segment j (j a multiple of F^(r+1)) adds the slots j + i F^r, i < F, into its own.  Groups are
+// disjoint, so no second buffer and no synchronisation inside a round; buckets with a single segment
+// cost one early exit per round.  After ceil(log_F(max segments)) rounds slot 0 holds the bucket sum.
+static const uint32_t COMBINE_F = 8;
+template <class F>
+struct CombineRoundArgs {
+    size_t nthreads;  // upper bound on tasks
+    XYZZ<F>* partials;
+    const uint32_t* task_bucket;
+    const uint32_t* seg_off;
+    const uint32_t* nseg;
+    const uint32_t* ntasks;
+    uint32_t stride;  // COMBINE_F^round
+};
+template <class F>
+MB_HD void combine_round_body(const CombineRoundArgs<F>& a, size_t tid) {
+    if (tid >= *a.ntasks) return;
+    const uint32_t b = a.task_bucket[tid];
+    const uint32_t ns = a.nseg[b];
+    if (ns <= a.stride) return;  // nothing left to fold in this bucket
+    const uint32_t j = (uint32_t)tid - a.seg_off[b];
+    if (j % (a.stride * COMBINE_F) != 0 || j + a.stride >= ns) return;
+    XYZZ<F> acc = a.partials[tid];
+    MB_NOUNROLL
+    for (uint32_t i = 1; i < COMBINE_F; ++i) {
+        uint64_t idx = (uint64_t)j + (uint64_t)i * a.stride;
+        if (idx >= ns) break;
+        xyzz_add_cold(acc, a.partials[tid + (size_t)i * a.stride]);
+    }
+    a.partials[tid] = acc;
+}
+MB_HD void combine_round_g1_body(const CombineRoundArgs<Fp>& a, size_t tid) { combine_round_body<Fp>(a, tid); }
+MB_HD void combine_round_g2_body(const CombineRoundArgs<Fp2>& a, size_t tid) { combine_round_body<Fp2>(a, tid); }
+MB_K_RED_G1(msm_combine_round_g1, CombineRoundArgs<Fp>, combine_round_g1_body, 128)
+MB_K_RED_G2(msm_combine_round_g2, CombineRoundArgs<Fp2>, combine_round_g2_body, 64)
+
 template <class F>
 struct CombineArgs {
     size_t nthreads;  // buckets
     const XYZZ<F>* partials;
     const uint32_t* seg_off;
-    const uint32_t* nseg;
     XYZZ<F>* buckets;
+    uint32_t add_into;  // 1: buckets already hold the sums of earlier slabs of the same MSM
 };
 template <class F>
 MB_HD void combine_body(const CombineArgs<F>& a, size_t tid) {
-    uint32_t t0 = a.seg_off[tid], ns = a.nseg[tid];
-    XYZZ<F> acc = a.partials[t0];
-    MB_NOUNROLL
-    for (uint32_t j = 1; j < ns; ++j) xyzz_add_cold(acc, a.partials[t0 + j]);
-    a.buckets[tid] = acc;
+    XYZZ<F> v = a.partials[a.seg_off[tid]];
+    if (a.add_into) {
+        XYZZ<F> acc = a.buckets[tid];
+        xyzz_add_cold(acc, v);
+        v = acc;
+    }
+    a.buckets[tid] = v;
 }
 MB_HD void combine_g1_body(const CombineArgs<Fp>& a, size_t tid) { combine_body<Fp>(a, tid); }
 MB_HD void combine_g2_body(const CombineArgs<Fp2>& a, size_t tid) { combine_body<Fp2>(a, tid); }
@@ -425,6 +468,12 @@ inline void launch_acc<Fp>(const AccArgs<Fp>& a, cudaStream_t s) { launch_msm_ac
 template <>
 inline void launch_acc<Fp2>(const AccArgs<Fp2>& a, cudaStream_t s) { launch_msm_accumulate_g2(a, s); }
 template <class F>
+inline void launch_combine_round(const CombineRoundArgs<F>& a, cudaStream_t s);
+template <>
+inline void launch_combine_round<Fp>(const CombineRoundArgs<Fp>& a, cudaStream_t s) { launch_msm_combine_round_g1(a, s); }
+template <>
+inline void launch_combine_round<Fp2>(const CombineRoundArgs<Fp2>& a, cudaStream_t s) { launch_msm_combine_round_g2(a, s); }
+template <class F>
 inline void launch_combine(const CombineArgs<F>& a, cudaStream_t s);
 template <>
 inline void launch_combine<Fp>(const CombineArgs<Fp>& a, cudaStream_t s) { launch_msm_combine_g1(a, s); }
@@ -448,8 +497,24 @@ inline void launch_horner<Fp2>(const HornerArgs<Fp2>& a, cudaStream_t s) { launc
 // addition, one shared inversion per launch -- were built and measured in round 1: 434 / 416 / 402
 // proofs/s with 1 / 2 / 3 rounds against 484 without, profiles/r01_pair_rounds_v2_sweep.jsonl; removed.)
 template <class F>
+void msm_reduce_buckets(const MsmClass& k, uint32_t n_inst, XYZZ<F>* out, MsmScratch& w, cudaStream_t s);
+
+// Steps 1-4 and the fold of split buckets: w.buckets receives (add_into: is increased by) the bucket sums.
+template <class F>
+void msm_accumulate_buckets(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t pool_stride,
+                            MsmScratch& w, cudaStream_t s, bool add_into);
+
+template <class F>
 void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t pool_stride, XYZZ<F>* out,
              MsmScratch& w, cudaStream_t s) {
+    if (n_inst == 0) return;
+    msm_accumulate_buckets<F>(k, n_inst, pool, pool_stride, w, s, false);
+    msm_reduce_buckets<F>(k, n_inst, out, w, s);
+}
+
+template <class F>
+void msm_accumulate_buckets(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t pool_stride,
+                            MsmScratch& w, cudaStream_t s, bool add_into) {
     if (n_inst == 0) return;
     size_t nbuckets = (size_t)n_inst * k.inst_stride;
     size_t max_entries = (size_t)n_inst * k.n_bases * k.nwin;
@@ -578,14 +643,32 @@ void msm_run(const MsmClass& k, uint32_t n_inst, const uint32_t* pool, size_t po
         cudaEventDestroy(e1);
     }
 #endif
+    {   // fold the partial sums of split buckets: rounds of fan-in COMBINE_F, enough for the fullest possible bucket
+        uint64_t worst = ((uint64_t)k.n_bases * (k.precomp ? k.nwin : 1) + SEG_LEN - 1) / SEG_LEN;
+        CombineRoundArgs<F> cr;
+        cr.nthreads = max_tasks;
+        cr.partials = w.partials.as<XYZZ<F>>();
+        cr.task_bucket = w.task_bucket.as<uint32_t>();
+        cr.seg_off = w.seg_off.as<uint32_t>();
+        cr.nseg = w.nseg.as<uint32_t>();
+        cr.ntasks = w.ntasks.as<uint32_t>();
+        for (uint64_t stride = 1; stride < worst; stride *= COMBINE_F) {
+            cr.stride = (uint32_t)stride;
+            launch_combine_round<F>(cr, s);
+        }
+    }
     CombineArgs<F> ca;
     ca.nthreads = nbuckets;
     ca.partials = w.partials.as<XYZZ<F>>();
     ca.seg_off = w.seg_off.as<uint32_t>();
-    ca.nseg = w.nseg.as<uint32_t>();
     ca.buckets = w.buckets.as<XYZZ<F>>();
+    ca.add_into = add_into ? 1 : 0;
     launch_combine<F>(ca, s);
+}
 
+// Step 5: out[inst] = sum over the bucket sets of sum_b b * S_b (times the window weights).
+template <class F>
+void msm_reduce_buckets(const MsmClass& k, uint32_t n_inst, XYZZ<F>* out, MsmScratch& w, cudaStream_t s) {
     // reduction levels
     uint32_t jobs = n_inst * k.nsets;
     uint32_t n_w = k.nb + 1, n_p = k.n_ones, stride_in = k.set_stride;

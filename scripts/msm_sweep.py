@@ -1,21 +1,21 @@
 #!/usr/bin/env python
-"""BASELINE config 3: standalone BLS12-381 G1 MSM sweep, bases range-split over
-the ranks, 192-byte projective partials all-gathered and added.
+"""BASELINE config 3: standalone BLS12-381 G1 MSM sweep, bases range-split over the GPUs, the 192-byte
+projective partials gathered on a device and added there (no host hop).
 
-  python scripts/msm_sweep.py --sizes 16 18 20              # one GPU
-  torchrun --nproc-per-node 8 scripts/msm_sweep.py ...      # bases split 8 ways
+  python scripts/msm_sweep.py --sizes 16 18 20 22 24                 # one GPU
+  torchrun --nproc-per-node 8 scripts/msm_sweep.py ...                # one rank per GPU, NCCL all-gather of device partials
+  python scripts/msm_sweep.py --devices 8 ...                         # ONE process, 8 GPUs behind the C ABI (peer copies)
 
-Bases are PRNG scalars times the generator (known discrete logs), so every
-result is checked in closed form against (sum s_i k_i) * G when --check is
-given (oracle, rank 0).  Reports per size: wall time of the whole MSM call
-with device-resident bases (scalars uploaded inside), the device time of the
-bucket-accumulation kernels, and the achieved algorithmic GB/s (128 N bytes).
+Bases are PRNG scalars times the generator (known discrete logs), so every result is checked in closed
+form against (sum s_i k_i) * G (oracle, rank 0) unless --no-check.  Scalars sit in pinned host memory and
+are uploaded inside the timed call.  One JSON line per (size, scalar kind): wall time of the whole call,
+device time of the bucket-accumulation kernels, achieved algorithmic GB/s (128 N bytes).
+The measurement itself is bench.py's msm_sweep (the same function fills `configs.msm_sweep` of the bench line).
 """
 import argparse
 import json
 import os
 import sys
-import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -23,74 +23,34 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from masp_b200 import sharding, synthetic as syn  # noqa: E402
+import bench  # noqa: E402
 import masp_b200.prover as pv  # noqa: E402
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--sizes", type=int, nargs="+", default=[16, 18, 20, 22])
+    ap.add_argument("--sizes", type=int, nargs="+", default=[16, 18, 20, 22, 24])
     ap.add_argument("--kinds", nargs="+", default=["U", "W"])
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--devices", type=int, default=1, help="GPUs driven by this one process")
+    ap.add_argument("--no-check", action="store_true")
     args = ap.parse_args()
-    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    pv.init(local)
-    peak = 6547.5
-    try:
-        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    except Exception:
-        pass
-    for log_n in args.sizes:
-        n = 1 << log_n
-        lo, hi = sharding.shard_range(n, rank, world)
-        bases = pv.synth_points(syn.STREAM_MSM_BASE, lo, hi - lo, 1)   # this rank's range only
-        gb = pv.G1Bases(bases, hi - lo)
-        del bases
-        for kind in args.kinds:
-            sc_all = syn.msm_scalars(n, kind)
-            sc = syn.limbs_to_bytes(sc_all[lo:hi])
-            times, acc_us = [], []
-            result = None
-            for rep in range(args.reps + 1):
-                pv.set_option("profile", 1)
-                torch.cuda.synchronize()
-                if world > 1:
-                    dist.barrier()
-                t0 = time.perf_counter()
-                partial = gb.msm_partial(sc)
-                if world > 1:
-                    parts = sharding._gather_bytes(partial, torch.device("cuda", local))
-                else:
-                    parts = [partial]
-                result = pv.g1_sum_partials(parts)
-                dt = time.perf_counter() - t0
-                if world > 1:
-                    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                    dt = float(t.item())
-                if rep:  # first repetition is warm-up
-                    times.append(dt)
-                    acc_us.append(pv.get_counter("acc_us"))
-                pv.set_option("profile", 0)
-            if rank == 0:
-                ok = None
-                if args.check:
-                    from oracle import c_oracle as co
-                    logs = syn.fr_uniform(syn.MASTER_SEED, syn.STREAM_MSM_BASE, n)
-                    dot = co.fr_dot(syn.limbs_to_bytes(sc_all), syn.limbs_to_bytes(logs), n)
-                    ok = result == co.g1_gen_mul(dot.to_bytes(32, "little"), 1)
-                best, acc = min(times), min(acc_us) * 1e-6
-                print(json.dumps({"config": "msm_g1_sweep", "log_n": log_n, "scalars": kind, "n_gpus": world,
-                                  "ms_total": 1e3 * best, "ms_accumulate_kernel": 1e3 * acc,
-                                  "gbs_total": 128.0 * n / best / 1e9,
-                                  "gbs_accumulate_kernel_per_gpu": 128.0 * (hi - lo) / acc / 1e9 if acc else None,
-                                  "frac_of_hbm_peak_kernel": 128.0 * (hi - lo) / acc / 1e9 / peak if acc else None,
-                                  "closed_form_ok": ok}), flush=True)
-        del gb
+    pv.init(list(range(args.devices)) if args.devices > 1 else local)
+    peak, _ = bench.measured_peak()
+    rows = bench.msm_sweep(pv, torch, dist, rank, world, args.devices, args.sizes, args.kinds, args.reps,
+                           check=not args.no_check)
+    if rank == 0:
+        for r in rows:
+            r["config"] = "msm_g1_sweep"
+            r["limit_ms_1.3x_acc_plus_5"] = 1.3 * r["ms_accumulate_kernel"] + 5.0
+            r["within_limit"] = r["ms_total"] <= r["limit_ms_1.3x_acc_plus_5"]
+            if r.get("gbs_accumulate_kernel_per_gpu"):
+                r["frac_of_hbm_peak_kernel"] = r["gbs_accumulate_kernel_per_gpu"] / peak
+            print(json.dumps(r), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -39,9 +39,28 @@ def test_msm(emu, oracle):
     b2 = oracle.g2_gen_mul(syn.limbs_to_bytes(logs[:12]), 12)
     sc = ib(rand_scalars(12, 77))
     assert emu.msm_g2(b2, sc, 12) == oracle.msm_g2(b2, sc, 12)
+    # a very heavy bucket: 9 000 equal scalars put 9 000 entries = 71 segments into one bucket per window, which the
+    # tree combine folds in three rounds of fan-in 8 (71 -> 9 -> 2 -> 1); 520 is the two-round case (5 segments)
+    big_logs = syn.fr_uniform(syn.MASTER_SEED, 12, 9000)
+    big = oracle.g1_gen_mul(syn.limbs_to_bytes(big_logs), 9000)
+    for n, val in ((9000, 5), (9000, syn.R_INT - 2), (520, 3)):
+        sc = ib([val] * n)
+        assert emu.msm_g1(big[:96 * n], sc, n) == oracle.msm_g1(big[:96 * n], sc, n), (n, val)
     parts = [emu.G1Bases(bases[96 * lo:96 * hi], hi - lo).msm_partial(ib(rand_scalars(300, 5))[32 * lo:32 * hi])
              for lo, hi in ((0, 100), (100, 300))]
     assert emu.g1_sum_partials(parts) == oracle.msm_g1(bases, ib(rand_scalars(300, 5)), 300)
+    # slabs: a standalone MSM uploads / sorts / accumulates its scalars in slabs (two buffers in turn) and
+    # adds the slab partials; 300 scalars in slabs of <= 64 is five slabs, 7 a single short one
+    emu.set_option("msm_slab", 64)
+    try:
+        for n in (300, 65, 64, 7):
+            sc = ib(rand_scalars(n, n + 1))
+            assert emu.msm_g1(bases[:96 * n], sc, n) == oracle.msm_g1(bases[:96 * n], sc, n), n
+        sc = ib(rand_scalars(12, 78))
+        emu.set_option("msm_slab", 5)
+        assert emu.msm_g2(b2, sc, 12) == oracle.msm_g2(b2, sc, 12)
+    finally:
+        emu.set_option("msm_slab", 1 << 22)
 
 
 @pytest.mark.slow
