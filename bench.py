@@ -350,7 +350,7 @@ def load_traffic():
         return None
 
 
-def msm_sweep(pv, torch, dist, rank, world, ndev, sizes, kinds, reps, check):
+def msm_sweep(pv, torch, dist, rank, world, ndev, sizes, kinds, reps, check, emit=None):
     """BASELINE config 3: one G1 MSM of 2^k bases, range-split over the GPUs (world ranks under
     torch.distributed, or ndev devices inside this process); partials meet on a device (NCCL
     all-gather of 192-byte XYZZ points, or NVLink peer copies) and are added there."""
@@ -410,6 +410,8 @@ def msm_sweep(pv, torch, dist, rank, world, ndev, sizes, kinds, reps, check):
                     del logs
                 best = min(times)
                 acc = min(acc_us) * 1e-6 / max(1, ndev)   # the counter adds up the devices of this process
+                if emit:
+                    emit("msm 2^%d %s: %.2f ms" % (log_n, kind, 1e3 * best))
                 out.append({"log_n": log_n, "scalars": kind, "n_gpus": world * ndev, "ms_total": 1e3 * best,
                             "ms_accumulate_kernel": 1e3 * acc,
                             "gbs_total": 128.0 * n / best / 1e9,

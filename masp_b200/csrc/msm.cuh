@@ -256,6 +256,11 @@ struct AccArgs {
     const uint32_t* order;  // thread -> task
     const uint32_t* ntasks;
     XYZZ<F>* partials;      // per task
+    // slabs of one standalone MSM share their buckets: a bucket's first segment starts from the sum the
+    // earlier slabs left there instead of the identity (nullptr on the proving path and for the first slab)
+    const XYZZ<F>* carry;
+    const uint32_t* task_bucket;
+    const uint32_t* seg_off;
 };
 template <class F>
 MB_HD void acc_body(const AccArgs<F>& a, size_t tid) {
@@ -263,6 +268,10 @@ MB_HD void acc_body(const AccArgs<F>& a, size_t tid) {
     uint32_t t = a.order[tid];
     uint32_t n = a.task_len[t];
     XYZZ<F> acc = XYZZ<F>::inf();
+    if (a.carry) {
+        const uint32_t b = a.task_bucket[t];
+        if (a.seg_off[b] == t) acc = a.carry[b];
+    }
     const uint32_t* e = a.entries + a.task_start[t];
     MB_NOUNROLL
     for (uint32_t i = 0; i < n; ++i) {
@@ -333,17 +342,10 @@ struct CombineArgs {
     const XYZZ<F>* partials;
     const uint32_t* seg_off;
     XYZZ<F>* buckets;
-    uint32_t add_into;  // 1: buckets already hold the sums of earlier slabs of the same MSM
 };
 template <class F>
 MB_HD void combine_body(const CombineArgs<F>& a, size_t tid) {
-    XYZZ<F> v = a.partials[a.seg_off[tid]];
-    if (a.add_into) {
-        XYZZ<F> acc = a.buckets[tid];
-        xyzz_add_cold(acc, v);
-        v = acc;
-    }
-    a.buckets[tid] = v;
+    a.buckets[tid] = a.partials[a.seg_off[tid]];
 }
 MB_HD void combine_g1_body(const CombineArgs<Fp>& a, size_t tid) { combine_body<Fp>(a, tid); }
 MB_HD void combine_g2_body(const CombineArgs<Fp2>& a, size_t tid) { combine_body<Fp2>(a, tid); }
@@ -618,6 +620,9 @@ void msm_accumulate_buckets(const MsmClass& k, uint32_t n_inst, const uint32_t* 
     aa.order = w.order.as<uint32_t>();
     aa.ntasks = w.ntasks.as<uint32_t>();
     aa.partials = w.partials.as<XYZZ<F>>();
+    aa.carry = add_into ? w.buckets.as<XYZZ<F>>() : nullptr;
+    aa.task_bucket = w.task_bucket.as<uint32_t>();
+    aa.seg_off = w.seg_off.as<uint32_t>();
 #ifndef MB200_EMU
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_msm_profile.enabled) {
@@ -662,7 +667,6 @@ void msm_accumulate_buckets(const MsmClass& k, uint32_t n_inst, const uint32_t* 
     ca.partials = w.partials.as<XYZZ<F>>();
     ca.seg_off = w.seg_off.as<uint32_t>();
     ca.buckets = w.buckets.as<XYZZ<F>>();
-    ca.add_into = add_into ? 1 : 0;
     launch_combine<F>(ca, s);
 }
 

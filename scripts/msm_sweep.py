@@ -42,7 +42,7 @@ def main():
     pv.init(list(range(args.devices)) if args.devices > 1 else local)
     peak, _ = bench.measured_peak()
     rows = bench.msm_sweep(pv, torch, dist, rank, world, args.devices, args.sizes, args.kinds, args.reps,
-                           check=not args.no_check)
+                           check=not args.no_check, emit=lambda m: print(m, file=sys.stderr, flush=True))
     if rank == 0:
         for r in rows:
             r["config"] = "msm_g1_sweep"

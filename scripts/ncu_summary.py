@@ -64,12 +64,7 @@ def main():
         except Exception:
             pass
     open(out, "w").write("\n".join(lines) + "\n")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    tpath = os.path.join(root, "profiles", "ncu_traffic.json")
-    old = json.load(open(tpath)) if os.path.exists(tpath) else {}
-    old.update(traffic)
-    json.dump(old, open(tpath, "w"), indent=1, sort_keys=True)
-    print("wrote", out, "and", tpath)
+    print("wrote", out, {k: v for k, v in traffic.items()})
 
 
 if __name__ == "__main__":
