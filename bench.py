@@ -379,6 +379,7 @@ def msm_sweep(pv, torch, dist, rank, world, ndev, sizes, kinds, reps, check, emi
                 gb.msm_partial_into(sc, mine)
                 if world > 1:
                     dist.all_gather_into_tensor(gathered, mine)   # NCCL, device buffers: K6's exchange
+                    torch.cuda.current_stream().synchronize()     # the library adds on its own stream: order it after NCCL's
                     return pv.g1_sum_partials_device(gathered, world)
                 return pv.g1_sum_partials_device(mine, 1)
             for rep in range(reps + 2):
