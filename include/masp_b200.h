@@ -173,6 +173,9 @@ int mb200_circuit_matrix(const mb200_circuit* c, int which, uint32_t* rowptr, ui
  * reference's synthesis would have returned an error for this witness. */
 int mb200_circuit_synthesize(const mb200_circuit* c, size_t n, const uint8_t* witnesses, uint8_t* inputs_out,
                              uint8_t* aux_out, int n_threads);
+/* 1 when witnesses are generated eight at a time on AVX-512 IFMA lanes (csrc/circuits_simd.cpp), 0 when the
+ * CPU lacks IFMA (or MB200_WITNESS_SCALAR=1) and the one-at-a-time generator runs.  Same bytes either way. */
+int mb200_circuit_simd(void);
 /* The Pedersen hash exactly as the circuits compute it (circuit/pedersen_hash.rs:19-103 in witness
  * form = masp_primitives::sapling::pedersen_hash): bits[0..6) are the personalization, the rest the
  * message, one byte per bit; the result is the affine (u, v) of the hash point.  The reference's

@@ -19,7 +19,7 @@ SYMBOLS = [
     "mb200_fr_mul_device", "mb200_set_option", "mb200_get_counter", "mb200_selftest", "mb200_bench_fpmul", "mb200_bench_latency",
     "mb200_strerror", "mb200_last_error",
     "mb200_circuit_new", "mb200_circuit_free", "mb200_circuit_info", "mb200_circuit_hash", "mb200_circuit_densities",
-    "mb200_circuit_matrix", "mb200_circuit_synthesize", "mb200_circuit_rows", "mb200_circuit_root", "mb200_pedersen_hash", "mb200_params_bind_circuit", "mb200_prove_batch_witness", "mb200_verify_batch", "mb200_verify_proofs", "mb200_verify_proofs_batch",
+    "mb200_circuit_matrix", "mb200_circuit_synthesize", "mb200_circuit_simd", "mb200_circuit_rows", "mb200_circuit_root", "mb200_pedersen_hash", "mb200_params_bind_circuit", "mb200_prove_batch_witness", "mb200_verify_batch", "mb200_verify_proofs", "mb200_verify_proofs_batch",
 ]
 
 
@@ -86,6 +86,7 @@ def bind(path):
     L.mb200_circuit_densities.argtypes = [vp, u8p, u8p, u8p]
     L.mb200_circuit_matrix.argtypes = [vp, c.c_int, vp, vp, vp]
     L.mb200_circuit_synthesize.argtypes = [vp, sz, u8p, u8p, u8p, c.c_int]
+    L.mb200_circuit_simd.argtypes = []
     L.mb200_circuit_root.argtypes = [vp, u8p, u8p]
     L.mb200_pedersen_hash.argtypes = [u8p, sz, u8p, u8p]
     L.mb200_circuit_rows.argtypes = [vp, sz, vp, vp, vp, vp, vp]

@@ -22,6 +22,10 @@ EMU_LIB = os.path.join(ROOT, "tests", "emu", "libmasp_b200_emu.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC"]
 UNIT_TIMEOUT = int(os.environ.get("MB200_BUILD_TIMEOUT", "1500"))
+# host-only units with their own instruction-set flags: the eight-lane witness generator (AVX-512 IFMA);
+# csrc/circuits.cu checks the CPU at run time before calling into it
+SIMD_FLAGS = ["-mavx512f", "-mavx512ifma", "-mavx512vl", "-mavx512dq", "-mavx512bw"]
+CPP_UNITS = {"circuits_simd.cpp": SIMD_FLAGS}
 
 
 def _units():
@@ -64,6 +68,13 @@ def build(force=False, verbose=False):
         if force or _newer(obj, [src] + hdrs):
             cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", "-o", obj, src]
             jobs.append((u, cmd, os.path.join(OBJ, u[:-3] + ".log")))
+    cxx = os.environ.get("CXX", "g++")
+    for u, flags in CPP_UNITS.items():
+        src = os.path.join(CSRC, u)
+        obj = os.path.join(OBJ, u[:-4] + ".o")
+        if force or _newer(obj, [src] + hdrs):
+            cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-pthread"] + flags + ["-c", "-o", obj, src]
+            jobs.append((u, cmd, os.path.join(OBJ, u[:-4] + ".log")))
     if jobs:
         with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
             futs = {u: ex.submit(_compile, cmd, log) for u, cmd, log in jobs}
@@ -71,14 +82,14 @@ def build(force=False, verbose=False):
                 dt = f.result()
                 if verbose:
                     print("  %-14s %.1fs" % (u, dt))
-    objs = [os.path.join(OBJ, u[:-3] + ".o") for u in _units()]
+    objs = [os.path.join(OBJ, u[:-3] + ".o") for u in _units()] + [os.path.join(OBJ, u[:-4] + ".o") for u in CPP_UNITS]
     if jobs or _newer(LIB, objs):
         subprocess.check_call([nvcc] + ARCH + ["-shared", "-cudart", "static", "-o", LIB] + objs)
     return LIB
 
 
 def build_emu(force=False):
-    srcs = [os.path.join(CSRC, u) for u in _units()]
+    srcs = [os.path.join(CSRC, u) for u in _units()] + [os.path.join(CSRC, u) for u in CPP_UNITS]
     if not force and not _newer(EMU_LIB, srcs + _headers()):
         return EMU_LIB
     os.makedirs(os.path.dirname(EMU_LIB), exist_ok=True)
@@ -87,8 +98,9 @@ def build_emu(force=False):
     base = ["g++", "-x", "c++", "-DMB200_EMU", "-O2", "-std=c++17", "-fPIC", "-pthread", "-Wno-unused-function"]
 
     def one(src):
-        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        subprocess.check_call(base + ["-c", "-o", obj, src])
+        name = os.path.basename(src)
+        obj = os.path.join(objdir, name.rsplit(".", 1)[0] + ".o")
+        subprocess.check_call(base + CPP_UNITS.get(name, []) + ["-c", "-o", obj, src])
         return obj
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(one, srcs))

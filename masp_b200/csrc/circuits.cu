@@ -7,7 +7,7 @@
 #include <thread>
 
 #include "host/circuit_obj.hpp"
-#include "host/circuits_host.hpp"
+#include "host/gadgets.hpp"
 #include "rt.cuh"
 
 using namespace mbh;
@@ -122,48 +122,6 @@ std::string structural_hash(const CS& cs) {
     return s;
 }
 
-// --- witness decoding (layout documented in include/masp_b200.h) ---
-struct Reader {
-    const uint8_t* p;
-    bool ok = true;
-    Fr fr() {
-        Fr x = Fr::zero();
-        if (!Fr::from_bytes(p, x)) ok = false;
-        p += 32;
-        return x;
-    }
-    JPoint point() {
-        JPoint q;
-        q.u = fr();
-        q.v = fr();
-        return q;
-    }
-    void words(uint64_t w[4]) {
-        memcpy(w, p, 32);
-        p += 32;
-    }
-    // a Jubjub scalar: the circuits allocate 252 bits for it (JUBJUB_FR_BITS), anything above is an error
-    void jscalar(uint64_t w[4]) {
-        words(w);
-        if (w[3] >> 60) ok = false;
-    }
-    uint64_t u64() {
-        uint64_t w[4];
-        words(w);
-        if (w[1] | w[2] | w[3]) ok = false;
-        return w[0];
-    }
-    void path(uint32_t depth, std::vector<AuthNode>& out) {
-        out.resize(depth);
-        for (uint32_t i = 0; i < depth; ++i) {
-            out[i].sibling = fr();
-            uint64_t b = u64();
-            if (b > 1) ok = false;
-            out[i].is_right = b != 0;
-        }
-    }
-};
-
 size_t witness_size(int kind, uint32_t depth) {
     switch (kind) {
         case MB200_CIRCUIT_SPEND: return 32 * (12 + 2 * (size_t)depth);
@@ -173,47 +131,11 @@ size_t witness_size(int kind, uint32_t depth) {
     return 0;
 }
 
-// false: a field is out of range
+// one witness on the scalar field; false: a field is out of range
 bool run_circuit(CS& cs, int kind, uint32_t depth, const uint8_t* w) {
-    Reader r{w};
-    if (kind == MB200_CIRCUIT_SPEND) {
-        SpendWitness s;
-        s.ak = r.point();
-        r.jscalar(s.nsk);
-        s.g_d = r.point();
-        s.asset_generator = r.point();
-        s.value = r.u64();
-        r.jscalar(s.rcv);
-        r.jscalar(s.rcm);
-        r.jscalar(s.ar);
-        s.anchor = r.fr();
-        r.path(depth, s.path);
-        if (!r.ok) return false;
-        spend_circuit(cs, s);
-    } else if (kind == MB200_CIRCUIT_OUTPUT) {
-        OutputWitness o;
-        memcpy(o.asset_identifier, r.p, 32);
-        r.p += 32;
-        o.asset_generator = r.point();
-        o.value = r.u64();
-        r.jscalar(o.rcv);
-        o.g_d = r.point();
-        o.pk_d = r.point();
-        r.jscalar(o.rcm);
-        r.jscalar(o.esk);
-        if (!r.ok) return false;
-        output_circuit(cs, o);
-    } else {
-        ConvertWitness c;
-        c.asset_generator = r.point();
-        c.value = r.u64();
-        r.jscalar(c.rcv);
-        c.anchor = r.fr();
-        r.path(depth, c.path);
-        if (!r.ok) return false;
-        convert_circuit(cs, c);
-    }
-    return true;
+    bool bad = false;
+    run_circuit_lanes<ScalarPolicy>(cs, kind, depth, &w, &bad);
+    return !bad;
 }
 
 }  // namespace
@@ -311,9 +233,9 @@ int mb200_pedersen_hash(const uint8_t* bits, size_t n_bits, uint8_t u_out[32], u
         CS cs;
         bool pers[6];
         for (int i = 0; i < 6; ++i) pers[i] = bits[i] != 0;
-        Bits in;
-        for (size_t i = 6; i < n_bits; ++i) in.push_back(Boolean::from_bit(AllocatedBit::alloc(cs, bits[i] != 0)));
-        EdwardsPoint h = pedersen_hash(cs, pers, in);
+        GS::Bits in;
+        for (size_t i = 6; i < n_bits; ++i) in.push_back(GS::Boolean::from_bit(GS::AllocatedBit::alloc(cs, bits[i] != 0)));
+        GS::EdwardsPoint h = GS::pedersen_hash(cs, pers, in);
         if (cs.failed) return MB200_ESYNTH;
         h.u.value.to_bytes(u_out);
         h.v.value.to_bytes(v_out);
@@ -336,21 +258,80 @@ int mb200_circuit_root(const mb200_circuit* c, const uint8_t* witness, uint8_t r
     return MB200_OK;
 }
 
+// csrc/circuits_simd.cpp: eight witnesses per call on AVX-512 IFMA lanes
+int mbh_simd_synthesize8(int kind, uint32_t depth, const uint8_t* const witnesses[8], uint8_t* const inputs_out[8],
+                         uint8_t* const aux_out[8], uint32_t expect_inputs, uint32_t expect_aux, uint8_t status[8]);
+void mbh_simd_warm(void);
+int mbh_simd_compiled(void);
+
+// 1: witnesses are generated eight at a time on AVX-512 IFMA lanes; 0: one at a time (CPU without
+// IFMA, or MB200_WITNESS_SCALAR=1 for A/B measurements)
+int mb200_circuit_simd(void) {
+    static const int on = [] {
+        const char* e = getenv("MB200_WITNESS_SCALAR");
+        if (e && *e && *e != '0') return 0;
+        if (!mbh_simd_compiled()) return 0;
+#if defined(__x86_64__) && (defined(__GNUC__) || defined(__clang__))
+        __builtin_cpu_init();
+        return (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512ifma") &&
+                __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512dq") &&
+                __builtin_cpu_supports("avx512bw")) ? 1 : 0;
+#else
+        return 0;
+#endif
+    }();
+    return on;
+}
+
 int mb200_circuit_synthesize(const mb200_circuit* c, size_t n, const uint8_t* witnesses, uint8_t* inputs_out,
                              uint8_t* aux_out, int n_threads) {
     if (!c || (n && (!witnesses || !inputs_out || !aux_out))) return MB200_EINVAL;
     if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
     if (n_threads < 1) n_threads = 1;
-    if ((size_t)n_threads > n) n_threads = (int)n;
+    const bool simd = mb200_circuit_simd() != 0 && n >= 2;
+    // work items: groups of eight witnesses (SIMD; the last group is padded by repeating its last
+    // witness into scratch outputs) or single witnesses (scalar)
+    const size_t group = simd ? 8 : 1;
+    const size_t n_items = (n + group - 1) / group;
+    if ((size_t)n_threads > n_items) n_threads = (int)n_items;
     (void)JJ();  // build the window tables before the workers start
     (void)K();
+    (void)GS::T();
+    if (simd) mbh_simd_warm();
     std::atomic<size_t> next(0);
     std::atomic<int> status(MB200_OK);
     auto work = [&]() {
         try {
+            std::vector<uint8_t> scratch_in, scratch_aux;  // outputs of padding lanes
             for (;;) {
-                size_t i = next.fetch_add(1);
-                if (i >= n) break;
+                size_t item = next.fetch_add(1);
+                if (item >= n_items) break;
+                if (simd) {
+                    const size_t first = item * 8, live = std::min<size_t>(8, n - first);
+                    const uint8_t* w[8];
+                    uint8_t *io[8], *ao[8];
+                    if (live < 8) {
+                        scratch_in.resize((size_t)c->n_inputs * 32);
+                        scratch_aux.resize((size_t)c->n_aux * 32);
+                    }
+                    for (size_t k = 0; k < 8; ++k) {
+                        size_t i = first + std::min(k, live - 1);
+                        w[k] = witnesses + i * c->witness_bytes;
+                        io[k] = k < live ? inputs_out + i * (size_t)c->n_inputs * 32 : scratch_in.data();
+                        ao[k] = k < live ? aux_out + i * (size_t)c->n_aux * 32 : scratch_aux.data();
+                    }
+                    uint8_t st[8];
+                    if (mbh_simd_synthesize8(c->kind, c->depth, w, io, ao, c->n_inputs, c->n_aux, st) != 0) {
+                        status = MB200_ENOMEM;
+                        continue;
+                    }
+                    for (size_t k = 0; k < live; ++k) {
+                        if (st[k] == 1) status = MB200_ESCALAR;
+                        else if (st[k]) status = MB200_ESYNTH;
+                    }
+                    continue;
+                }
+                const size_t i = item;
                 CS cs;
                 cs.aux.reserve(c->n_aux);
                 if (!run_circuit(cs, c->kind, c->depth, witnesses + i * c->witness_bytes)) {
@@ -368,6 +349,8 @@ int mb200_circuit_synthesize(const mb200_circuit* c, size_t n, const uint8_t* wi
             }
         } catch (const std::bad_alloc&) {
             status = MB200_ENOMEM;
+        } catch (...) {
+            status = MB200_ESYNTH;
         }
     };
     // nothing may unwind across the C boundary: a worker that cannot be spawned (std::system_error)

@@ -4,7 +4,7 @@
 #include <string>
 #include <vector>
 
-#include "r1cs_host.hpp"
+#include "gadgets.hpp"
 
 struct mb200_circuit {
     int kind = 0;          // MB200_CIRCUIT_*

@@ -31,6 +31,7 @@
 // Generator coordinates are data from masp_primitives/src/constants.rs:50-251.
 #pragma once
 #include <algorithm>
+#include <cstring>
 #include <string>
 #include <type_traits>
 #include <utility>
@@ -160,8 +161,9 @@ struct CS {
     }
 };
 
-struct Words256 {  // one 256-bit little-endian integer (a Jubjub scalar, 32 identifier bytes)
-    uint64_t w[4];
+template <int LANES>
+struct WordsN {  // one 256-bit little-endian integer per lane (a Jubjub scalar, 32 identifier bytes)
+    uint64_t w[LANES][4];
 };
 
 struct ScalarPolicy {
@@ -171,8 +173,12 @@ struct ScalarPolicy {
     typedef Fr C;         // a table constant used as a VALUE (coefficients of LCs are always Fr)
     typedef LC L;
     typedef CS Sink;
-    typedef Words256 W;
+    typedef WordsN<1> W;
     static constexpr bool RECORDS = true;
+    static constexpr int LANES = 1;
+    static F from_words(const uint64_t w[1][4]) { return Fr::from_words(w[0]); }
+    static U ufrom(const uint64_t v[1]) { return v[0]; }
+    static B bfrom(const bool b[1]) { return b[0]; }
     static C konst(const Fr& f) { return f; }
     static F lift(const C& c) { return c; }
     static F zero() { return Fr::zero(); }
@@ -188,7 +194,7 @@ struct ScalarPolicy {
         v.to_words(w);
         for (int i = 0; i < n; ++i) out[i] = (w[i >> 6] >> (i & 63)) & 1;
     }
-    static B wbit(const W& w, int i) { return (w.w[i >> 6] >> (i & 63)) & 1; }
+    static B wbit(const W& w, int i) { return (w.w[0][i >> 6] >> (i & 63)) & 1; }
     static U uzero() { return 0; }
     static U uset(U v, B b, int i) { return v | ((uint64_t)(b ? 1 : 0) << i); }
     static B ubit(U v, int i) { return (v >> i) & 1; }
@@ -1393,6 +1399,128 @@ struct G {
         cm.u.inputize(cs);
     }
 };
+
+// ---------------------------------------------------------------------------
+// witness decoding (layout documented in include/masp_b200.h), P::LANES witnesses at a time
+// ---------------------------------------------------------------------------
+enum { CIRCUIT_SPEND = 0, CIRCUIT_OUTPUT = 1, CIRCUIT_CONVERT = 2 };  // = MB200_CIRCUIT_*
+
+template <class P>
+struct WitnessReader {
+    static constexpr int N = P::LANES;
+    typedef G<P> Gp;
+    const uint8_t* p[N];
+    bool bad[N];  // per lane: a field is out of range
+    explicit WitnessReader(const uint8_t* const* w) {
+        for (int k = 0; k < N; ++k) {
+            p[k] = w[k];
+            bad[k] = false;
+        }
+    }
+    void raw(uint64_t w[N][4]) {
+        for (int k = 0; k < N; ++k) {
+            memcpy(w[k], p[k], 32);
+            p[k] += 32;
+        }
+    }
+    typename P::F fr() {
+        uint64_t w[N][4];
+        raw(w);
+        for (int k = 0; k < N; ++k)
+            if (Fr::geq_mod(w[k])) {
+                bad[k] = true;
+                memset(w[k], 0, 32);
+            }
+        return P::from_words(w);
+    }
+    typename Gp::JPoint point() {
+        typename Gp::JPoint q;
+        q.u = fr();
+        q.v = fr();
+        return q;
+    }
+    typename P::W words() {
+        typename P::W r;
+        raw(r.w);
+        return r;
+    }
+    // a Jubjub scalar: the circuits allocate 252 bits for it (JUBJUB_FR_BITS), anything above is an error
+    typename P::W jscalar() {
+        typename P::W r = words();
+        for (int k = 0; k < N; ++k)
+            if (r.w[k][3] >> 60) bad[k] = true;
+        return r;
+    }
+    void u64_raw(uint64_t v[N]) {
+        uint64_t w[N][4];
+        raw(w);
+        for (int k = 0; k < N; ++k) {
+            if (w[k][1] | w[k][2] | w[k][3]) bad[k] = true;
+            v[k] = w[k][0];
+        }
+    }
+    typename P::U u64() {
+        uint64_t v[N];
+        u64_raw(v);
+        return P::ufrom(v);
+    }
+    void path(uint32_t depth, std::vector<typename Gp::AuthNode>& out) {
+        out.resize(depth);
+        for (uint32_t i = 0; i < depth; ++i) {
+            out[i].sibling = fr();
+            uint64_t v[N];
+            u64_raw(v);
+            bool b[N];
+            for (int k = 0; k < N; ++k) {
+                if (v[k] > 1) bad[k] = true;
+                b[k] = v[k] != 0;
+            }
+            out[i].is_right = P::bfrom(b);
+        }
+    }
+};
+
+// Runs the circuit over P::LANES witnesses; bad_out[k]: witness k has a field out of range (its lane
+// ran on zeros in that field's place and its outputs mean nothing).
+template <class P>
+void run_circuit_lanes(typename P::Sink& cs, int kind, uint32_t depth, const uint8_t* const* w, bool* bad_out) {
+    typedef G<P> Gp;
+    WitnessReader<P> r(w);
+    if (kind == CIRCUIT_SPEND) {
+        typename Gp::SpendWitness s;
+        s.ak = r.point();
+        s.nsk = r.jscalar();
+        s.g_d = r.point();
+        s.asset_generator = r.point();
+        s.value = r.u64();
+        s.rcv = r.jscalar();
+        s.rcm = r.jscalar();
+        s.ar = r.jscalar();
+        s.anchor = r.fr();
+        r.path(depth, s.path);
+        Gp::spend_circuit(cs, s);
+    } else if (kind == CIRCUIT_OUTPUT) {
+        typename Gp::OutputWitness o;
+        o.asset_identifier = r.words();
+        o.asset_generator = r.point();
+        o.value = r.u64();
+        o.rcv = r.jscalar();
+        o.g_d = r.point();
+        o.pk_d = r.point();
+        o.rcm = r.jscalar();
+        o.esk = r.jscalar();
+        Gp::output_circuit(cs, o);
+    } else {
+        typename Gp::ConvertWitness c;
+        c.asset_generator = r.point();
+        c.value = r.u64();
+        c.rcv = r.jscalar();
+        c.anchor = r.fr();
+        r.path(depth, c.path);
+        Gp::convert_circuit(cs, c);
+    }
+    for (int k = 0; k < P::LANES; ++k) bad_out[k] = r.bad[k];
+}
 
 typedef G<ScalarPolicy> GS;
 

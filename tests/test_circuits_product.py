@@ -156,6 +156,62 @@ def test_bad_witnesses_are_rejected():
         c.synthesize([inst.pack()[:-1]])
 
 
+
+def _cheap_instance(kind, depth, rnd):
+    """A witness without the Python oracle (its anchor is arbitrary: witness generation does not need a satisfied circuit)."""
+    js = lambda: rnd.randrange(mc.JUBJUB_ORDER)
+    path = [(rnd.randrange(R), bool(rnd.getrandbits(1))) for _ in range(depth)]
+    vc = C.ValueCommitmentOpening(AG, rnd.getrandbits(64), js())
+    if kind == C.CONVERT:
+        return C.Convert(vc, path, rnd.randrange(R))
+    if kind == C.OUTPUT:
+        return C.Output(vc, IDENT, G_D, mc.jj_mul(G_D, rnd.randrange(1, 1 << 60)), js(), js())
+    return C.Spend(vc, AK, js(), G_D, js(), js(), path, rnd.randrange(R))
+
+
+@pytest.mark.parametrize("kind,depth,n", [(C.SPEND, 32, 11), (C.OUTPUT, 0, 9), (C.CONVERT, 32, 17), (C.CONVERT, 3, 2)])
+def test_simd_witnesses_equal_scalar_witnesses(kind, depth, n):
+    """The eight-lane AVX-512 IFMA generator (csrc/circuits_simd.cpp: batches of two or more) against the
+    one-witness scalar generator (a batch of one always takes it): same inputs and aux, byte for byte,
+    including the padded last group and lanes holding the extreme values."""
+    from masp_b200._lib import lib
+    if not lib().mb200_circuit_simd():
+        pytest.skip("this CPU has no AVX-512 IFMA: the scalar generator is the only one")
+    rnd = random.Random(1000 * kind + n)
+    c = C.Circuit(kind, depth)
+    insts = [_cheap_instance(kind, depth, rnd) for _ in range(n)]
+    insts[1].value_commitment.value = 0
+    insts[n - 1].value_commitment.value = 2 ** 64 - 1
+    insts[0].value_commitment.randomness = mc.JUBJUB_ORDER - 1
+    inputs, aux = c.synthesize(insts, threads=2)
+    for k, inst in enumerate(insts):
+        i1, a1 = c.synthesize([inst])
+        assert inputs[32 * c.n_inputs * k:32 * c.n_inputs * (k + 1)] == i1, k
+        assert aux[32 * c.n_aux * k:32 * c.n_aux * (k + 1)] == a1, k
+
+
+def test_simd_lane_errors_are_reported():
+    """One bad lane fails the call with the scalar path's code, wherever in the group it sits."""
+    from masp_b200._lib import lib, Mb200Error
+    if not lib().mb200_circuit_simd():
+        pytest.skip("this CPU has no AVX-512 IFMA")
+    rnd = random.Random(31)
+    c = C.Circuit(C.CONVERT, 2)
+    for lane in (0, 5, 8):
+        packed = [_cheap_instance(C.CONVERT, 2, rnd).pack() for _ in range(10)]
+        w = bytearray(packed[lane])
+        w[0:32] = R.to_bytes(32, "little")
+        packed[lane] = bytes(w)
+        with pytest.raises(Mb200Error) as e:
+            c.synthesize(packed)
+        assert e.value.code == -6
+        insts = [_cheap_instance(C.CONVERT, 2, rnd) for _ in range(10)]
+        insts[lane].value_commitment.asset_generator = (0, 1)   # small order: assert_nonzero fails
+        with pytest.raises(Mb200Error) as e:
+            c.synthesize(insts)
+        assert e.value.code == -7
+
+
 def _rows_check(circ_mod, kind, depth):
     c = circ_mod.Circuit(kind, depth)
     insts = [make_instance(kind, depth) for _ in range(2)]
