@@ -40,7 +40,26 @@ struct MsmClass {
     uint32_t inst_stride;  // nsets * set_stride
 };
 
-inline uint32_t msm_nwin(uint32_t c) { return (256 + c - 1) / c; }
+// Windows needed for a scalar in signed c-bit digits.  The digit walk first folds a scalar above
+// (r - 1) / 2 to r - s and flips the sign of all of its entries, so every scalar it decomposes is at
+// most (r - 1) / 2 < 2^254: ceil(254 / c) windows cover every bit, and the top digit never borrows
+// from a further window as long as its largest value plus the carry from below stays <= 2^(c-1)
+// (checked per c; otherwise one more window).  c = 17 -> 15 windows, c = 15 -> 17, where the unfolded
+// range 0 .. r - 1 needs 16 and 18: one bucket addition per full-width scalar less.
+inline uint32_t msm_nwin(uint32_t c) {
+    uint32_t h[8];  // (r - 1) / 2
+    for (int i = 0; i < 8; ++i) h[i] = FrCfg::half(i);
+    uint32_t nwin = (254 + c - 1) / c;
+    uint32_t lo = (nwin - 1) * c;  // first bit of the top window
+    uint64_t top = 0;              // largest top digit: ((r - 1) / 2) >> lo
+    for (int i = 7; i >= 0; --i) {
+        if ((uint32_t)(32 * i + 31) < lo) break;
+        if ((uint32_t)(32 * i) >= lo) top |= (uint64_t)h[i] << (32 * i - lo);
+        else top |= (uint64_t)(h[i] >> (lo - 32 * i));
+    }
+    if (top + 1 > (1ull << (c - 1))) ++nwin;
+    return nwin;
+}
 
 inline MsmClass msm_make_class(const void* table, const uint32_t* sel, uint32_t n_bases, uint32_t c, bool precomp,
                                uint32_t n_ones = 0) {
@@ -85,6 +104,25 @@ MB_HD void digit_emit(const DigitArgs& a, size_t bucket, uint32_t entry) {
     }
 }
 
+// one window: raw digit + carry -> signed digit, borrow for the next window, entry
+template <int MODE>
+MB_HD void digit_window(const DigitArgs& a, const MsmClass& k, uint32_t d, uint32_t w, uint32_t& carry, uint32_t flip,
+                        size_t b0, uint32_t base) {
+    d += carry;
+    uint32_t neg = 0;
+    carry = 0;
+    if (d > k.nb) {  // use d - 2^c, borrow one from the next window
+        d = (1u << k.c) - d;
+        neg = 1;
+        carry = 1;
+    }
+    neg ^= flip;
+    if (d == 0) return;
+    uint32_t set = k.precomp ? 0 : w;
+    uint32_t tw = k.precomp ? w : 0;
+    digit_emit<MODE>(a, b0 + (size_t)set * k.set_stride + d, ((tw * k.n_bases + base) << 1) | neg);
+}
+
 template <int MODE>
 MB_HD void digit_body(const DigitArgs& a, size_t tid) {
     const MsmClass& k = a.k;
@@ -93,39 +131,71 @@ MB_HD void digit_body(const DigitArgs& a, size_t tid) {
     const uint32_t* sp = a.pool + (inst * a.pool_stride + (k.sel ? k.sel[base] : base)) * 8;
     uint32_t s[8];
     uint32_t any_hi = 0;
-    MB_UNROLL
+#ifdef MB200_EMU
     for (int i = 0; i < 8; ++i) s[i] = sp[i];
+#else
+    {   // pool entries are 32-byte aligned: two 16-byte loads
+        const uint4 lo4 = reinterpret_cast<const uint4*>(sp)[0], hi4 = reinterpret_cast<const uint4*>(sp)[1];
+        s[0] = lo4.x; s[1] = lo4.y; s[2] = lo4.z; s[3] = lo4.w;
+        s[4] = hi4.x; s[5] = hi4.y; s[6] = hi4.z; s[7] = hi4.w;
+    }
+#endif
     MB_UNROLL
     for (int i = 1; i < 8; ++i) any_hi |= s[i];
     if (any_hi == 0 && s[0] == 0) return;
     size_t b0 = inst * k.inst_stride;
+    // s > (r - 1) / 2: walk r - s and negate every entry (msm_nwin counts windows for the folded range)
+    uint32_t flip = 0;
+    {
+        uint32_t gt = 0, decided = 0;
+        MB_UNROLL
+        for (int i = 7; i >= 0; --i) {
+            uint32_t hi = FrCfg::half(i);
+            uint32_t g = s[i] > hi ? 1u : 0u, l = s[i] < hi ? 1u : 0u;
+            gt |= g & ~decided;
+            decided |= g | l;
+        }
+        flip = gt & 1u;
+        if (flip) {
+            uint32_t borrow = 0;
+            MB_UNROLL
+            for (int i = 0; i < 8; ++i) {
+                uint32_t m = FrCfg::mod(i);
+                uint32_t d0 = m - s[i];
+                uint32_t b1 = m < s[i] ? 1u : 0u;
+                uint32_t d1 = d0 - borrow;
+                uint32_t b2 = d0 < borrow ? 1u : 0u;
+                s[i] = d1;
+                borrow = b1 | b2;
+            }
+            any_hi = 0;
+            MB_UNROLL
+            for (int i = 1; i < 8; ++i) any_hi |= s[i];
+        }
+    }
     if (any_hi == 0 && s[0] == 1) {
-        digit_emit<MODE>(a, b0 + k.nb + 1 + base % k.n_ones, base << 1);
+        digit_emit<MODE>(a, b0 + k.nb + 1 + base % k.n_ones, (base << 1) | flip);
         return;
     }
-    uint32_t carry = 0;
+    // windows are peeled off a 64-bit buffer refilled limb by limb: the limbs stay in registers
+    // (indexing s[] by a run-time window position had put the scalar into local memory)
+    uint32_t carry = 0, w = 0, nbits = 0;
     const uint32_t c = k.c, mask = (1u << c) - 1;
-    for (uint32_t w = 0; w < k.nwin; ++w) {
-        uint32_t bit = w * c;
-        uint32_t limb = bit >> 5, off = bit & 31;
-        uint32_t d = 0;
-        if (limb < 8) {
-            d = s[limb] >> off;
-            if (off + c > 32 && limb + 1 < 8) d |= s[limb + 1] << (32 - off);
-            d &= mask;
+    uint64_t buf = 0;
+    MB_UNROLL
+    for (int i = 0; i < 8; ++i) {
+        buf |= (uint64_t)s[i] << nbits;
+        nbits += 32;
+        while (nbits >= c && w < k.nwin) {
+            digit_window<MODE>(a, k, (uint32_t)buf & mask, w, carry, flip, b0, base);
+            buf >>= c;
+            nbits -= c;
+            ++w;
         }
-        d += carry;
-        uint32_t neg = 0;
-        carry = 0;
-        if (d > k.nb) {  // use d - 2^c, borrow one from the next window
-            d = (1u << c) - d;
-            neg = 1;
-            carry = 1;
-        }
-        if (d == 0) continue;
-        uint32_t set = k.precomp ? 0 : w;
-        uint32_t tw = k.precomp ? w : 0;
-        digit_emit<MODE>(a, b0 + (size_t)set * k.set_stride + d, ((tw * k.n_bases + base) << 1) | neg);
+    }
+    for (; w < k.nwin; ++w) {  // the partly filled top window, then windows that only receive a carry
+        digit_window<MODE>(a, k, (uint32_t)buf & mask, w, carry, flip, b0, base);
+        buf = 0;
     }
 }
 MB_HD void digit_count_body(const DigitArgs& a, size_t tid) { digit_body<0>(a, tid); }
@@ -134,47 +204,141 @@ MB_K_MSM_G1(msm_count, DigitArgs, digit_count_body, 256)
 MB_K_MSM_G1(msm_scatter, DigitArgs, digit_scatter_body, 256)
 
 // ---------------------------------------------------------------------------
-// 2: exclusive scan of `counts` -> offsets and cursor (three small kernels)
+// 2: exclusive scan of `counts` -> offsets and cursor.  Three block-cooperative kernels over
+// tiles of SCAN_TILE elements: tile sums (coalesced 16-byte loads, shuffle reduction), an exclusive
+// scan of the tile sums by one block, and the tile-local scan that writes offsets (and the scatter
+// cursor) back with 16-byte stores.  (Round 1 gave every thread 512 consecutive elements: three
+// launches of ~110 / 44 / 40 us for 2.1 M buckets, strided across the warp; this form moves the
+// same 25 MB at streaming speed.)
 // ---------------------------------------------------------------------------
 struct ScanArgs {
-    size_t nthreads;
     const uint32_t* counts;
     uint32_t* offsets;
-    uint32_t* cursor;
-    uint32_t* partial;  // one per chunk
+    uint32_t* cursor;   // may be nullptr
+    uint32_t* partial;  // one per tile
     size_t n;           // elements
-    uint32_t chunk;     // elements per thread
 };
-MB_HD void scan_sum_body(const ScanArgs& a, size_t tid) {
-    size_t lo = tid * a.chunk, hi = lo + a.chunk;
-    if (hi > a.n) hi = a.n;
-    uint32_t s = 0;
-    for (size_t i = lo; i < hi; ++i) s += a.counts[i];
-    a.partial[tid] = s;
-}
-MB_HD void scan_top_body(const ScanArgs& a, size_t) {
-    size_t nchunks = (a.n + a.chunk - 1) / a.chunk;
+static const uint32_t SCAN_THREADS = 256, SCAN_PER_THREAD = 8, SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+inline size_t scan_tiles(size_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+void launch_scan(const ScanArgs& a, cudaStream_t s);  // all three steps, in order, on s
+
+#ifdef MB_DEFINE_MSM_G1
+#ifdef MB200_EMU
+void launch_scan(const ScanArgs& a, cudaStream_t) {
     uint32_t run = 0;
-    for (size_t i = 0; i < nchunks; ++i) {
-        uint32_t v = a.partial[i];
-        a.partial[i] = run;
-        run += v;
-    }
-}
-MB_HD void scan_write_body(const ScanArgs& a, size_t tid) {
-    size_t lo = tid * a.chunk, hi = lo + a.chunk;
-    if (hi > a.n) hi = a.n;
-    uint32_t run = a.partial[tid];
-    for (size_t i = lo; i < hi; ++i) {
+    for (size_t i = 0; i < a.n; ++i) {
         uint32_t v = a.counts[i];
         a.offsets[i] = run;
         if (a.cursor) a.cursor[i] = run;
         run += v;
     }
+    ::mb::g_launches += 3;
 }
-MB_K_MSM_G1(scan_sum, ScanArgs, scan_sum_body, 128)
-MB_K_MSM_G1(scan_top, ScanArgs, scan_top_body, 32)
-MB_K_MSM_G1(scan_write, ScanArgs, scan_write_body, 128)
+#else
+// this thread's SCAN_PER_THREAD consecutive elements (zero beyond n); buffers come from cudaMalloc,
+// so element 8 k is 32-byte aligned
+__device__ __forceinline__ void scan_load(const uint32_t* src, size_t n, size_t first, uint32_t v[SCAN_PER_THREAD]) {
+    if (first + SCAN_PER_THREAD <= n) {
+        uint4 x = *reinterpret_cast<const uint4*>(src + first), y = *reinterpret_cast<const uint4*>(src + first + 4);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+        v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+        for (uint32_t i = 0; i < SCAN_PER_THREAD; ++i) v[i] = first + i < n ? src[first + i] : 0u;
+    }
+}
+// exclusive prefix of `mine` over the block's threads (thread order); *total: the block's sum
+__device__ __forceinline__ uint32_t scan_block_exclusive(uint32_t mine, uint32_t* total) {
+    __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < SCAN_THREADS / 32; ++w) {
+        uint32_t ws = warp_sums[w];
+        before += w < warp ? ws : 0u;
+        all += ws;
+    }
+    __syncthreads();  // warp_sums may be reused by the caller's next tile
+    *total = all;
+    return before + incl - mine;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const ScanArgs a) {
+    uint32_t v[SCAN_PER_THREAD];
+    scan_load(a.counts, a.n, (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_PER_THREAD, v);
+    uint32_t sum = 0, total;
+#pragma unroll
+    for (uint32_t i = 0; i < SCAN_PER_THREAD; ++i) sum += v[i];
+    scan_block_exclusive(sum, &total);
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_offsets(const ScanArgs a, size_t ntiles) {
+    uint32_t carry = 0;  // one block walks the tile sums, SCAN_TILE at a time
+    for (size_t base = 0; base < ntiles; base += SCAN_TILE) {
+        uint32_t v[SCAN_PER_THREAD];
+        const size_t first = base + (size_t)threadIdx.x * SCAN_PER_THREAD;
+        scan_load(a.partial, ntiles, first, v);
+        uint32_t sum = 0, total;
+#pragma unroll
+        for (uint32_t i = 0; i < SCAN_PER_THREAD; ++i) sum += v[i];
+        uint32_t run = carry + scan_block_exclusive(sum, &total);
+#pragma unroll
+        for (uint32_t i = 0; i < SCAN_PER_THREAD; ++i) {
+            if (first + i < ntiles) a.partial[first + i] = run;
+            run += v[i];
+        }
+        carry += total;
+    }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_write(const ScanArgs a) {
+    uint32_t v[SCAN_PER_THREAD];
+    const size_t first = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_PER_THREAD;
+    scan_load(a.counts, a.n, first, v);
+    uint32_t sum = 0, total;
+#pragma unroll
+    for (uint32_t i = 0; i < SCAN_PER_THREAD; ++i) sum += v[i];
+    uint32_t run = a.partial[blockIdx.x] + scan_block_exclusive(sum, &total);
+    uint32_t o[SCAN_PER_THREAD];
+#pragma unroll
+    for (uint32_t i = 0; i < SCAN_PER_THREAD; ++i) {
+        o[i] = run;
+        run += v[i];
+    }
+    if (first + SCAN_PER_THREAD <= a.n) {
+        const uint4 x = make_uint4(o[0], o[1], o[2], o[3]), y = make_uint4(o[4], o[5], o[6], o[7]);
+        *reinterpret_cast<uint4*>(a.offsets + first) = x;
+        *reinterpret_cast<uint4*>(a.offsets + first + 4) = y;
+        if (a.cursor) {
+            *reinterpret_cast<uint4*>(a.cursor + first) = x;
+            *reinterpret_cast<uint4*>(a.cursor + first + 4) = y;
+        }
+    } else {
+#pragma unroll
+        for (uint32_t i = 0; i < SCAN_PER_THREAD; ++i)
+            if (first + i < a.n) {
+                a.offsets[first + i] = o[i];
+                if (a.cursor) a.cursor[first + i] = o[i];
+            }
+    }
+}
+void launch_scan(const ScanArgs& a, cudaStream_t s) {
+    if (!a.n) return;
+    const size_t ntiles = scan_tiles(a.n);
+    scan_tile_sums<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(a);
+    scan_tile_offsets<<<1, SCAN_THREADS, 0, s>>>(a, ntiles);
+    scan_tile_write<<<(unsigned)ntiles, SCAN_THREADS, 0, s>>>(a);
+    MB_CUDA(cudaGetLastError());
+    ::mb::g_launches += 3;
+}
+#endif
+#endif
 
 // ---------------------------------------------------------------------------
 // 3b: tasks.  A bucket's entry list is cut into segments of at most SEG_LEN
@@ -222,9 +386,26 @@ struct OrderArgs {
     uint32_t* hist;   // ORDER_CAP bins, zeroed
     uint32_t* order;  // task ids, longest first
 };
+// Almost every task of a proof-sized launch has the same length, so the 32 lanes of a warp hit the
+// same bin: the lanes with equal bins elect a leader that adds their count once and hands out ranks
+// (one L2 atomic per warp and bin instead of 32 serialised on one address).
+MB_HD uint32_t order_bin_add(uint32_t* hist, uint32_t bin) {
+#if defined(__CUDA_ARCH__)
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, bin);
+    const unsigned lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if ((int)lane == leader) base = atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+#else
+    return MB_ATOMIC_ADD(&hist[bin], 1u);
+#endif
+}
 MB_HD void order_hist_body(const OrderArgs& a, size_t tid) {
     if (tid >= *a.ntasks) return;
-    MB_ATOMIC_ADD(&a.hist[SEG_LEN - a.task_len[tid]], 1u);
+    order_bin_add(a.hist, SEG_LEN - a.task_len[tid]);
 }
 MB_HD void order_scan_body(const OrderArgs& a, size_t) {
     uint32_t run = 0;
@@ -236,7 +417,7 @@ MB_HD void order_scan_body(const OrderArgs& a, size_t) {
 }
 MB_HD void order_scatter_body(const OrderArgs& a, size_t tid) {
     if (tid >= *a.ntasks) return;
-    uint32_t pos = MB_ATOMIC_ADD(&a.hist[SEG_LEN - a.task_len[tid]], 1u);
+    uint32_t pos = order_bin_add(a.hist, SEG_LEN - a.task_len[tid]);
     a.order[pos] = (uint32_t)tid;
 }
 MB_K_MSM_G1(order_hist, OrderArgs, order_hist_body, 256)
@@ -459,7 +640,6 @@ struct MsmProfile {  // optional CUDA-event timing of the accumulate kernel (all
 };
 extern MsmProfile g_msm_profile;
 
-static const uint32_t SCAN_CHUNK = 512;
 // reduction fan-in (log2): wide at level 0, narrow above it -- swept on B200 (profiles/r01_reduce_fanin_sweep.jsonl)
 static const uint32_t RED_LOG_T0 = 3, RED_LOG_T1 = 2;
 
@@ -522,7 +702,7 @@ void msm_accumulate_buckets(const MsmClass& k, uint32_t n_inst, const uint32_t* 
     size_t max_entries = (size_t)n_inst * k.n_bases * k.nwin;
     if (max_entries >= (1ull << 32) || (size_t)k.nwin * k.n_bases >= (1ull << 31))
         fail(MB200_EINVAL, "MSM too large for 32-bit entry indices%s (%ld entries)", "", (long)max_entries);
-    size_t nchunks = (nbuckets + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    size_t nchunks = scan_tiles(nbuckets);
     w.counts.ensure(nbuckets * 4);
     w.offsets.ensure(nbuckets * 4);
     w.cursor.ensure(nbuckets * 4);
@@ -547,13 +727,7 @@ void msm_accumulate_buckets(const MsmClass& k, uint32_t n_inst, const uint32_t* 
     sa.cursor = w.cursor.as<uint32_t>();
     sa.partial = w.partial.as<uint32_t>();
     sa.n = nbuckets;
-    sa.chunk = SCAN_CHUNK;
-    sa.nthreads = nchunks;
-    launch_scan_sum(sa, s);
-    sa.nthreads = 1;
-    launch_scan_top(sa, s);
-    sa.nthreads = nchunks;
-    launch_scan_write(sa, s);
+    launch_scan(sa, s);
 
     launch_msm_scatter(da, s);
 
@@ -589,13 +763,7 @@ void msm_accumulate_buckets(const MsmClass& k, uint32_t n_inst, const uint32_t* 
     sg.cursor = nullptr;
     sg.partial = w.partial.as<uint32_t>();
     sg.n = nbuckets;
-    sg.chunk = SCAN_CHUNK;
-    sg.nthreads = nchunks;
-    launch_scan_sum(sg, s);
-    sg.nthreads = 1;
-    launch_scan_top(sg, s);
-    sg.nthreads = nchunks;
-    launch_scan_write(sg, s);
+    launch_scan(sg, s);
     launch_seg_fill(ga, s);
 
     dev_memset(w.ohist.p, 0, ORDER_CAP * 4, s);

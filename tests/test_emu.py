@@ -158,7 +158,12 @@ def test_msm_special_bases(emu, oracle):
     seq = [pts[0], pts[0], pts[0], neg(pts[0]), pts[1], neg(pts[1]), inf, pts[2], pts[2], inf, pts[3], pts[3], pts[3], pts[3]]
     b = b"".join(seq)
     for scalars in ([5] * len(seq), [syn.R_INT - 1] * len(seq), [1] * len(seq), list(range(len(seq))),
-                    [7, 7, 9, 7, 3, 3, 5, 1, 1, 0, 2, 2, 2, 2]):
+                    [7, 7, 9, 7, 3, 3, 5, 1, 1, 0, 2, 2, 2, 2],
+                    # either side of the fold at (r - 1) / 2 (the digit walk decomposes r - s above it) and the
+                    # values whose folded image is 1 or 2 (the "ones" buckets with a negated entry)
+                    [(syn.R_INT - 1) // 2, (syn.R_INT + 1) // 2, (syn.R_INT - 1) // 2 - 1, (syn.R_INT + 1) // 2 + 1,
+                     syn.R_INT - 1, syn.R_INT - 2, 2, 1, syn.R_INT - 1, 0, 1 << 254, (1 << 254) - 1, (1 << 253) + 1,
+                     syn.R_INT - (1 << 200)]):
         assert emu.msm_g1(b, ib(scalars), len(seq)) == oracle.msm_g1(b, ib(scalars), len(seq)), scalars
     b2 = oracle.g2_gen_mul(syn.limbs_to_bytes(logs[:3]), 3)
     q = [b2[192 * i:192 * (i + 1)] for i in range(3)]

@@ -85,7 +85,9 @@ def test_msm_g1_special_bases(gpu, oracle):
     neg = lambda p: p[:48] + ((syn_p() - int.from_bytes(p[48:], "big")) % syn_p()).to_bytes(48, "big")
     inf = bytes([0x40]) + bytes(95)
     seq = [pts[0], pts[0], pts[0], neg(pts[0]), pts[1], neg(pts[1]), inf, pts[2], pts[2], inf]
-    for scalars in ([5] * len(seq), [R - 1] * len(seq), [1] * len(seq), list(range(len(seq))), [7, 7, 9, 7, 3, 3, 5, 1, 1, 0]):
+    for scalars in ([5] * len(seq), [R - 1] * len(seq), [1] * len(seq), list(range(len(seq))), [7, 7, 9, 7, 3, 3, 5, 1, 1, 0],
+                    # either side of the fold at (r - 1) / 2 in the digit walk
+                    [(R - 1) // 2, (R + 1) // 2, (R - 1) // 2 - 1, (R + 1) // 2 + 1, R - 1, R - 2, 2, 1 << 254, (1 << 254) - 1, R - (1 << 200)]):
         b = b"".join(seq)
         assert gpu.msm_g1(b, ib(scalars), len(seq)) == oracle.msm_g1(b, ib(scalars), len(seq)), scalars
 
