@@ -354,11 +354,13 @@ struct Mont {
             e[i] = m - borrow;
             borrow = m < borrow ? 1u : 0u;
         }
+        // a chain of ~1.5 * 32 N dependent multiplications: the inlined body has two thirds of the
+        // out-of-line latency (profiles/r01_latency_microbench.txt) and this loop is its only copy per unit
         Mont r = one();
         MB_NOUNROLL
         for (int i = 32 * N - 1; i >= 0; --i) {
-            r = sqr(r);
-            if ((e[i >> 5] >> (i & 31)) & 1) r = mul(r, a);
+            r = mul_inline(r, r);
+            if ((e[i >> 5] >> (i & 31)) & 1) r = mul_inline(r, a);
         }
         return r;
     }
