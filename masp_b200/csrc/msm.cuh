@@ -559,7 +559,16 @@ struct RedArgs {
     uint32_t shift;       // doublings applied to acc at this level: level * log2(T)
     uint32_t level;
 };
-template <class F>
+// INL: additions and doublings inlined (ptxas overlaps their independent multiplications: about half the
+// latency of the out-of-line bodies per level, at ~10x the code).  The proving path keeps the out-of-line
+// form -- its reductions hide under other chunks' kernels and a small i-cache footprint matters more
+// there -- the standalone MSM, whose caller waits for exactly this chain, takes the inlined one.
+template <class F, bool INL>
+MB_HD void red_add(XYZZ<F>& acc, const XYZZ<F>& q) {
+    if (INL) xyzz_add(acc, q);
+    else xyzz_add_cold(acc, q);
+}
+template <class F, bool INL = false>
 MB_HD void red_body(const RedArgs<F>& a, size_t tid) {
     size_t job = tid / a.n_out;
     uint32_t k = (uint32_t)(tid - job * a.n_out);
@@ -570,22 +579,22 @@ MB_HD void red_body(const RedArgs<F>& a, size_t tid) {
         if (hi > a.n_weighted) hi = a.n_weighted;
         MB_NOUNROLL
         for (uint32_t j = hi; j-- > lo + 1;) {
-            xyzz_add_cold(run, X[j]);
-            xyzz_add_cold(acc, run);
+            red_add<F, INL>(run, X[j]);
+            red_add<F, INL>(acc, run);
         }
-        xyzz_add_cold(run, X[lo]);
+        red_add<F, INL>(run, X[lo]);
         MB_NOUNROLL
-        for (uint32_t d = 0; d < a.shift; ++d) acc = xyzz_dbl_cold(acc);
+        for (uint32_t d = 0; d < a.shift; ++d) acc = INL ? xyzz_dbl(acc) : xyzz_dbl_cold(acc);
         if (a.level > 0) {
             const XYZZ<F>* P = a.P + job * a.stride_in;
             MB_NOUNROLL
-            for (uint32_t j = lo; j < hi; ++j) xyzz_add_cold(acc, P[j]);
+            for (uint32_t j = lo; j < hi; ++j) red_add<F, INL>(acc, P[j]);
         }
     } else {  // level 0 only: a chunk of ones buckets, plain sum
         uint32_t lo = a.n_weighted + (k - a.n_wout) * a.T, hi = lo + a.T;
         if (hi > a.n_weighted + a.n_plain) hi = a.n_weighted + a.n_plain;
         MB_NOUNROLL
-        for (uint32_t j = lo; j < hi; ++j) xyzz_add_cold(acc, X[j]);
+        for (uint32_t j = lo; j < hi; ++j) red_add<F, INL>(acc, X[j]);
     }
     a.Xo[job * a.stride_out + k] = run;
     a.Po[job * a.stride_out + k] = acc;
@@ -594,6 +603,8 @@ MB_HD void red_g1_body(const RedArgs<Fp>& a, size_t tid) { red_body<Fp>(a, tid);
 MB_HD void red_g2_body(const RedArgs<Fp2>& a, size_t tid) { red_body<Fp2>(a, tid); }
 MB_K_RED_G1(msm_reduce_g1, RedArgs<Fp>, red_g1_body, 64)
 MB_K_RED_G2(msm_reduce_g2, RedArgs<Fp2>, red_g2_body, 32)
+MB_HD void red_inl_g1_body(const RedArgs<Fp>& a, size_t tid) { red_body<Fp, true>(a, tid); }
+MB_K_MSM_G1(msm_reduce_inl_g1, RedArgs<Fp>, red_inl_g1_body, 32)
 
 // Horner over per-window results (non-precomputed tables only):
 // out[inst] = sum_w 2^(c w) * R[inst][w]
@@ -666,11 +677,14 @@ inline void launch_combine<Fp>(const CombineArgs<Fp>& a, cudaStream_t s) { launc
 template <>
 inline void launch_combine<Fp2>(const CombineArgs<Fp2>& a, cudaStream_t s) { launch_msm_combine_g2(a, s); }
 template <class F>
-inline void launch_red(const RedArgs<F>& a, cudaStream_t s);
+inline void launch_red(const RedArgs<F>& a, cudaStream_t s, bool latency);
 template <>
-inline void launch_red<Fp>(const RedArgs<Fp>& a, cudaStream_t s) { launch_msm_reduce_g1(a, s); }
+inline void launch_red<Fp>(const RedArgs<Fp>& a, cudaStream_t s, bool latency) {
+    if (latency) launch_msm_reduce_inl_g1(a, s);
+    else launch_msm_reduce_g1(a, s);
+}
 template <>
-inline void launch_red<Fp2>(const RedArgs<Fp2>& a, cudaStream_t s) { launch_msm_reduce_g2(a, s); }
+inline void launch_red<Fp2>(const RedArgs<Fp2>& a, cudaStream_t s, bool) { launch_msm_reduce_g2(a, s); }
 template <class F>
 inline void launch_horner(const HornerArgs<F>& a, cudaStream_t s);
 template <>
@@ -874,7 +888,7 @@ void msm_reduce_buckets(const MsmClass& k, uint32_t n_inst, XYZZ<F>* out, MsmScr
         w.lp[flip].ensure(ra.nthreads * sizeof(XYZZ<F>));
         ra.Xo = w.lx[flip].as<XYZZ<F>>();
         ra.Po = w.lp[flip].as<XYZZ<F>>();
-        launch_red<F>(ra, s);
+        launch_red<F>(ra, s, !k.precomp);  // no tables = a standalone MSM: its caller waits for this chain
         X = ra.Xo;
         P = ra.Po;
         n_w = ra.n_out;
