@@ -30,6 +30,7 @@ struct MsmClass {
     const void* table;     // Affine<F>[ (precomp ? nwin : 1) * n_bases ]
     const uint32_t* sel;   // n_bases: index of each base's scalar inside an instance's scalar pool (nullptr: base k <-> scalar k)
     uint32_t n_bases;
+    uint32_t table_stride; // bases per window strip of the table (= n_bases unless this class is a base range of a larger one)
     uint32_t c;            // window bits
     uint32_t nwin;         // windows: nwin * c >= 256
     uint32_t nb;           // 2^(c-1): digit magnitudes 1..nb
@@ -67,6 +68,7 @@ inline MsmClass msm_make_class(const void* table, const uint32_t* sel, uint32_t 
     k.table = table;
     k.sel = sel;
     k.n_bases = n_bases;
+    k.table_stride = n_bases;
     k.c = c;
     k.nwin = msm_nwin(c);
     k.nb = 1u << (c - 1);
@@ -79,6 +81,18 @@ inline MsmClass msm_make_class(const void* table, const uint32_t* sel, uint32_t 
     k.set_stride = k.nb + 1 + k.n_ones;
     k.inst_stride = k.nsets * k.set_stride;
     return k;
+}
+
+// Bases [lo, lo + cnt) of a table class as a class of their own: same windows, same bucket layout
+// (set_stride / inst_stride / n_ones are the parent's), so consecutive ranges can accumulate into one
+// bucket set (msm_accumulate_buckets with add_into).
+template <class F>
+inline MsmClass msm_base_range(const MsmClass& k, uint32_t lo, uint32_t cnt) {
+    MsmClass r = k;
+    r.table = (const Affine<F>*)k.table + lo;
+    r.sel = k.sel ? k.sel + lo : nullptr;
+    r.n_bases = cnt;
+    return r;  // table_stride stays the parent's
 }
 
 // ---------------------------------------------------------------------------
@@ -120,7 +134,7 @@ MB_HD void digit_window(const DigitArgs& a, const MsmClass& k, uint32_t d, uint3
     if (d == 0) return;
     uint32_t set = k.precomp ? 0 : w;
     uint32_t tw = k.precomp ? w : 0;
-    digit_emit<MODE>(a, b0 + (size_t)set * k.set_stride + d, ((tw * k.n_bases + base) << 1) | neg);
+    digit_emit<MODE>(a, b0 + (size_t)set * k.set_stride + d, ((tw * k.table_stride + base) << 1) | neg);
 }
 
 template <int MODE>
@@ -436,12 +450,14 @@ struct AccArgs {
     const uint32_t* task_len;
     const uint32_t* order;  // thread -> task
     const uint32_t* ntasks;
-    XYZZ<F>* partials;      // per task
-    // slabs of one standalone MSM share their buckets: a bucket's first segment starts from the sum the
-    // earlier slabs left there instead of the identity (nullptr on the proving path and for the first slab)
-    const XYZZ<F>* carry;
+    XYZZ<F>* partials;      // per task: the partial sums of buckets that were cut into several segments
+    XYZZ<F>* buckets;       // per bucket: a bucket with a single segment (almost all) is written here directly
+    // ranges of one MSM (slabs of a standalone MSM, base ranges of the H+L query) share their buckets: a
+    // bucket's first segment starts from the sum the earlier ranges left in `buckets` instead of the identity
+    uint32_t add_into;
     const uint32_t* task_bucket;
     const uint32_t* seg_off;
+    const uint32_t* nseg;
 };
 template <class F>
 MB_HD void acc_body(const AccArgs<F>& a, size_t tid) {
@@ -449,10 +465,9 @@ MB_HD void acc_body(const AccArgs<F>& a, size_t tid) {
     uint32_t t = a.order[tid];
     uint32_t n = a.task_len[t];
     XYZZ<F> acc = XYZZ<F>::inf();
-    if (a.carry) {
-        const uint32_t b = a.task_bucket[t];
-        if (a.seg_off[b] == t) acc = a.carry[b];
-    }
+    const uint32_t b = a.task_bucket[t];
+    const bool single = a.nseg[b] == 1;
+    if (a.add_into && (single || a.seg_off[b] == t)) acc = a.buckets[b];
     const uint32_t* e = a.entries + a.task_start[t];
     MB_NOUNROLL
     for (uint32_t i = 0; i < n; ++i) {
@@ -460,7 +475,8 @@ MB_HD void acc_body(const AccArgs<F>& a, size_t tid) {
         Affine<F> q = a.table[ent >> 1];
         xyzz_madd(acc, q, (ent & 1) != 0);
     }
-    a.partials[t] = acc;
+    if (single) a.buckets[b] = acc;  // no combine step for this bucket
+    else a.partials[t] = acc;
 }
 MB_HD void acc_g1_body(const AccArgs<Fp>& a, size_t tid) { acc_body<Fp>(a, tid); }
 MB_HD void acc_g2_body(const AccArgs<Fp2>& a, size_t tid) { acc_body<Fp2>(a, tid); }
@@ -522,11 +538,12 @@ struct CombineArgs {
     size_t nthreads;  // buckets
     const XYZZ<F>* partials;
     const uint32_t* seg_off;
+    const uint32_t* nseg;
     XYZZ<F>* buckets;
 };
 template <class F>
 MB_HD void combine_body(const CombineArgs<F>& a, size_t tid) {
-    a.buckets[tid] = a.partials[a.seg_off[tid]];
+    if (a.nseg[tid] > 1) a.buckets[tid] = a.partials[a.seg_off[tid]];  // single segments were written by the accumulate kernel
 }
 MB_HD void combine_g1_body(const CombineArgs<Fp>& a, size_t tid) { combine_body<Fp>(a, tid); }
 MB_HD void combine_g2_body(const CombineArgs<Fp2>& a, size_t tid) { combine_body<Fp2>(a, tid); }
@@ -718,7 +735,7 @@ void msm_accumulate_buckets(const MsmClass& k, uint32_t n_inst, const uint32_t* 
     if (n_inst == 0) return;
     size_t nbuckets = (size_t)n_inst * k.inst_stride;
     size_t max_entries = (size_t)n_inst * k.n_bases * k.nwin;
-    if (max_entries >= (1ull << 32) || (size_t)k.nwin * k.n_bases >= (1ull << 31))
+    if (max_entries >= (1ull << 32) || (size_t)k.nwin * k.table_stride >= (1ull << 31))
         fail(MB200_EINVAL, "MSM too large for 32-bit entry indices%s (%ld entries)", "", (long)max_entries);
     size_t nchunks = scan_tiles(nbuckets);
     w.counts.ensure(nbuckets * 4);
@@ -806,9 +823,11 @@ void msm_accumulate_buckets(const MsmClass& k, uint32_t n_inst, const uint32_t* 
     aa.order = w.order.as<uint32_t>();
     aa.ntasks = w.ntasks.as<uint32_t>();
     aa.partials = w.partials.as<XYZZ<F>>();
-    aa.carry = add_into ? w.buckets.as<XYZZ<F>>() : nullptr;
+    aa.buckets = w.buckets.as<XYZZ<F>>();
+    aa.add_into = add_into ? 1 : 0;
     aa.task_bucket = w.task_bucket.as<uint32_t>();
     aa.seg_off = w.seg_off.as<uint32_t>();
+    aa.nseg = w.nseg.as<uint32_t>();
 #ifndef MB200_EMU
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_msm_profile.enabled) {
@@ -852,6 +871,7 @@ void msm_accumulate_buckets(const MsmClass& k, uint32_t n_inst, const uint32_t* 
     ca.nthreads = nbuckets;
     ca.partials = w.partials.as<XYZZ<F>>();
     ca.seg_off = w.seg_off.as<uint32_t>();
+    ca.nseg = w.nseg.as<uint32_t>();
     ca.buckets = w.buckets.as<XYZZ<F>>();
     launch_combine<F>(ca, s);
 }
