@@ -201,9 +201,10 @@ static void msm_on_device_bases(Device& d, const Affine<F>* bases, const uint8_t
         return;
     }
     if (n >= (1ull << 31)) fail(MB200_EINVAL, "MSM of %s%ld bases is too large", "", (long)n);
-    // at least eight slabs once they are worth their fixed cost (>= 2^18 scalars each): only the first
+    // up to eight slabs once they are worth their fixed cost (every slab walks all bucket sets: >= 2^21
+    // scalars each, measured -- 2^18 made the 2^20 / 2^22 witness-like MSMs 30 % slower): only the first
     // slab's upload is exposed, the rest crosses PCIe under the previous slab's kernels
-    const size_t slab = std::min(g.msm_slab, std::max<size_t>((size_t)1 << 18, (n + 7) / 8));
+    const size_t slab = std::min(g.msm_slab, std::max<size_t>((size_t)1 << 21, (n + 7) / 8));
     const size_t nslab = (n + slab - 1) / slab;
     const size_t per = (n + nslab - 1) / nslab;  // equal slabs, each <= msm_slab
     for (int b = 0; b < (nslab > 1 ? 2 : 1); ++b) d.slab[b].ensure(per * 32);

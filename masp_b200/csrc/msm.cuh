@@ -30,7 +30,6 @@ struct MsmClass {
     const void* table;     // Affine<F>[ (precomp ? nwin : 1) * n_bases ]
     const uint32_t* sel;   // n_bases: index of each base's scalar inside an instance's scalar pool (nullptr: base k <-> scalar k)
     uint32_t n_bases;
-    uint32_t table_stride; // bases per window strip of the table (= n_bases unless this class is a base range of a larger one)
     uint32_t c;            // window bits
     uint32_t nwin;         // windows: nwin * c >= 256
     uint32_t nb;           // 2^(c-1): digit magnitudes 1..nb
@@ -68,7 +67,6 @@ inline MsmClass msm_make_class(const void* table, const uint32_t* sel, uint32_t 
     k.table = table;
     k.sel = sel;
     k.n_bases = n_bases;
-    k.table_stride = n_bases;
     k.c = c;
     k.nwin = msm_nwin(c);
     k.nb = 1u << (c - 1);
@@ -81,18 +79,6 @@ inline MsmClass msm_make_class(const void* table, const uint32_t* sel, uint32_t 
     k.set_stride = k.nb + 1 + k.n_ones;
     k.inst_stride = k.nsets * k.set_stride;
     return k;
-}
-
-// Bases [lo, lo + cnt) of a table class as a class of their own: same windows, same bucket layout
-// (set_stride / inst_stride / n_ones are the parent's), so consecutive ranges can accumulate into one
-// bucket set (msm_accumulate_buckets with add_into).
-template <class F>
-inline MsmClass msm_base_range(const MsmClass& k, uint32_t lo, uint32_t cnt) {
-    MsmClass r = k;
-    r.table = (const Affine<F>*)k.table + lo;
-    r.sel = k.sel ? k.sel + lo : nullptr;
-    r.n_bases = cnt;
-    return r;  // table_stride stays the parent's
 }
 
 // ---------------------------------------------------------------------------
@@ -134,7 +120,7 @@ MB_HD void digit_window(const DigitArgs& a, const MsmClass& k, uint32_t d, uint3
     if (d == 0) return;
     uint32_t set = k.precomp ? 0 : w;
     uint32_t tw = k.precomp ? w : 0;
-    digit_emit<MODE>(a, b0 + (size_t)set * k.set_stride + d, ((tw * k.table_stride + base) << 1) | neg);
+    digit_emit<MODE>(a, b0 + (size_t)set * k.set_stride + d, ((tw * k.n_bases + base) << 1) | neg);
 }
 
 template <int MODE>
@@ -735,7 +721,7 @@ void msm_accumulate_buckets(const MsmClass& k, uint32_t n_inst, const uint32_t* 
     if (n_inst == 0) return;
     size_t nbuckets = (size_t)n_inst * k.inst_stride;
     size_t max_entries = (size_t)n_inst * k.n_bases * k.nwin;
-    if (max_entries >= (1ull << 32) || (size_t)k.nwin * k.table_stride >= (1ull << 31))
+    if (max_entries >= (1ull << 32) || (size_t)k.nwin * k.n_bases >= (1ull << 31))
         fail(MB200_EINVAL, "MSM too large for 32-bit entry indices%s (%ld entries)", "", (long)max_entries);
     size_t nchunks = scan_tiles(nbuckets);
     w.counts.ensure(nbuckets * 4);

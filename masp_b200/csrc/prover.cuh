@@ -202,7 +202,6 @@ struct Params {
     DevBuf vk_g1, vk_g2, vk_ic, vk_ab;  // alpha_g1 | beta, gamma, delta (G2) | IC | Miller(-alpha, beta): the self-check
     R1csDev r1cs;                   // the circuit's matrices, when one is bound (mb200_params_bind_circuit)
     size_t table_bytes = 0;
-    uint32_t hl_slabs = 1;  // base ranges the H+L query is accumulated in (prove_chunk)
     // the density bitmaps the key was loaded with (empty = all dense): mb200_params_bind_circuit
     // compares them with the circuit's, position by position
     std::vector<uint8_t> a_aux_density, b_input_density, b_aux_density;
@@ -373,7 +372,6 @@ inline Params* params_load(const uint8_t* buf, size_t len, const uint8_t* a_aux_
 
     // window sizes: full-width share guessed from the reference circuits
     // (SURVEY §8 scalar make-up: ~1/3 of L, ~1/5 of A and B are full width)
-    P->hl_slabs = std::min<uint32_t>(64, std::max<uint32_t>(1, env_u32("MB200_HL_SLABS", 1)));
     uint32_t c_hl = env_u32("MB200_C_HL", choose_window(n_h + 0.33 * n_l));
     uint32_t c_a = env_u32("MB200_C_A", choose_window(0.25 * n_a + 16));
     uint32_t c_b1 = env_u32("MB200_C_B1", choose_window(0.25 * n_b1 + 16));
@@ -508,22 +506,14 @@ inline void prove_chunk(const Params& P, ProveCtx& x, const ProveInputs& in, siz
 
     h_pipeline(P.dom, count, (uint32_t)rows, x.abc.as<Fr>(), rows, x.pool.as<Fr>(), P.pool_stride, x.w0.as<Fr>(),
                x.w1.as<Fr>(), x.w2.as<Fr>(), x.w3.as<Fr>(), s);
-    if (P.hl_slabs <= 1) {
-        msm_run<Fp>(P.k_hl, count, pl, P.pool_stride, x.res_hl.as<G1XYZZ>(), x.msm, s);
-    } else {
-        // The H+L query in base ranges: every launch of the accumulate kernel walks each bucket's whole
-        // entry list, i.e. the whole 356 MB table, once per wave of resident blocks (~70 waves for a
-        // 64-proof chunk: 24.4 GB of DRAM reads measured, 13x the algorithmic bytes).  A range's strips
-        // (16 windows x n / slabs bases) fit the 126 MB L2, so each wave after the first finds them there;
-        // the ranges add into one bucket set and the reduction runs once.
-        const uint32_t n = P.k_hl.n_bases, S = P.hl_slabs;
-        for (uint32_t j = 0; j < S; ++j) {
-            const uint32_t lo = (uint32_t)((uint64_t)n * j / S), hi = (uint32_t)((uint64_t)n * (j + 1) / S);
-            if (hi == lo) continue;
-            msm_accumulate_buckets<Fp>(msm_base_range<Fp>(P.k_hl, lo, hi - lo), count, pl, P.pool_stride, x.msm, s, j > 0);
-        }
-        msm_reduce_buckets<Fp>(P.k_hl, count, x.res_hl.as<G1XYZZ>(), x.msm, s);
-    }
+    // (Measured and rejected, profiles/r02_ab_hl_base_ranges.jsonl: the H+L query in 4 / 8 / 16 base ranges
+    // whose table strips fit the L2.  Every launch of the accumulate kernel walks each bucket's whole entry
+    // list, i.e. the whole 356 MB table, once per wave of resident blocks -- ~70 waves per 64-proof chunk,
+    // 24.4 GB of DRAM reads, 13x the algorithmic bytes.  Ranges cut that to 14.9 GB and the L2 does hold
+    // the strips, but the kernel is bound by the multiplier, not by those reads: 508 / 499 / 492 proofs/s
+    // against 530 in one launch, because shorter tasks pay the accumulator load / store and the launch
+    // tail more often.)
+    msm_run<Fp>(P.k_hl, count, pl, P.pool_stride, x.res_hl.as<G1XYZZ>(), x.msm, s);
     // join: the assembly waits for the three side queries
 #ifndef MB200_EMU
     for (int i = 0; i < 3; ++i) {
