@@ -5,7 +5,7 @@
 // (`enforce` -> `eval`, called from Circuit::synthesize at
 // masp_proofs/src/circuit/sapling.rs:139-417, 419-596, convert.rs:29-128;
 // SURVEY.md §8 a-2).  The matrices are the same for every proof of a circuit,
-// so here they are recorded once (csrc/host/r1cs_host.hpp), kept in HBM as
+// so here they are recorded once (csrc/host/gadgets.hpp), kept in HBM as
 // CSR, and a = A z, b = B z, c = C z become a sparse matrix-vector product
 // over the proof's scalar pool: the host ships only the witness z.
 //
