@@ -473,7 +473,9 @@ MB_K_MSM_G1(msm_accumulate_g1, AccArgs<Fp>, acc_g1_body, 128)
 // 16 warps at 16 places of a 72 KB loop body); one lock-step block per SM with a barrier per
 // iteration (480: `no_instructions` gone, 94 k -> 1 k samples, but the multiplier drops from 82 % to
 // 78 % busy waiting at the barrier); lock-step with L2 prefetch (476) and with shared accumulators
-// (449).  The plain kernel at 166 registers and 12 warps per SM stays.
+// (449).  Round 2, profiles/r02_ab_acc_register_caps.jsonl: __maxnreg__ 152 / 144 / 136 with one-warp blocks
+// (13 / 14 / 15 resident warps, 24-80 B of spill): 523 / 519 / 526 against 531; one-warp blocks at the
+// full register count: 525.  The plain kernel at 164 registers and 12 warps per SM stays.
 MB_K_MSM_G2(msm_accumulate_g2, AccArgs<Fp2>, acc_g2_body, 64)
 // (its accumulator in shared memory -- 168 registers, 12 warps per SM instead of 255 and 8 --
 // measured 457 against 492 proofs/s: the ~800 LDS / STS per addition cost more than the spills.)
