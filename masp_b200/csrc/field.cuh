@@ -277,6 +277,46 @@ struct Mont {
         for (int i = 0; i < N; ++i) s.v[i] = borrow ? s.v[i] : t.v[i];
         return s;
     }
+    // r = (a * b + c * d) * 2^(-32N) mod p: both products share one accumulator pair and ONE Montgomery
+    // reduction (N rows of N wide multiplies saved against two multiplications and an addition).
+    // Bounds: the running value stays below 3p (2^32 + 1) < 2^(32 (N + 1)) -- the pair holds N + 1 limbs and
+    // 3p < 0.31 * 2^(32N) for both moduli used here -- and the result below (2 p^2 + 2^(32N) p) / 2^(32N)
+    // < 1.21 p, so one conditional subtraction brings it under p.
+    MB_HD static Mont sop2_inline(const Mont& a, const Mont& b, const Mont& c, const Mont& d) {
+        uint32_t ev[N], od[N];
+        MB_UNROLL
+        for (int j = 0; j < N; j += 2) {
+            ev[j] = mul_lo(a.v[j], b.v[0]);
+            ev[j + 1] = mul_hi(a.v[j], b.v[0]);
+            od[j] = mul_lo(a.v[j + 1], b.v[0]);
+            od[j + 1] = mul_hi(a.v[j + 1], b.v[0]);
+        }
+        row_acc(ev, od, c.v, d.v[0]);
+        row_redc(ev, od);
+        MB_UNROLL
+        for (int i = 1; i < N; i += 2) {
+            row_shift_acc(od, ev, a.v, b.v[i]);
+            row_acc(od, ev, c.v, d.v[i]);
+            row_redc(od, ev);
+            if (i + 1 < N) {
+                row_shift_acc(ev, od, a.v, b.v[i + 1]);
+                row_acc(ev, od, c.v, d.v[i + 1]);
+                row_redc(ev, od);
+            }
+        }
+        Mont s, t;
+        s.v[0] = add_cc(ev[0], od[1]);
+        MB_UNROLL
+        for (int i = 1; i < N - 1; ++i) s.v[i] = addc_cc(ev[i], od[i + 1]);
+        s.v[N - 1] = addc(ev[N - 1], 0);
+        t.v[0] = sub_cc(s.v[0], C::mod(0));
+        MB_UNROLL
+        for (int i = 1; i < N; ++i) t.v[i] = subc_cc(s.v[i], C::mod(i));
+        uint32_t borrow = subc(0, 0);
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) s.v[i] = borrow ? s.v[i] : t.v[i];
+        return s;
+    }
     // (A dedicated squaring -- cross products once, product-scanning reduction, 222 instead of 288
     // wide multiplies -- is exact but measured 2 % SLOWER inside the accumulation kernel: its
     // three-word column accumulator serialises what the row-wise form leaves independent.
