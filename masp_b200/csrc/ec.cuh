@@ -85,6 +85,15 @@ template <>
 MB_HD Fp madd_y3<Fp>(const Fp& R, const Fp& T, const Fp& Y1, const Fp& PPP) {
     return Fp::sop2_inline(R, T, Fp::neg(Y1), PPP);
 }
+#ifdef MB_FP2_SOP
+// Fp2: c0 = R0 T0 - R1 T1 - Y0 P0 + Y1 P1, c1 = R0 T1 + R1 T0 - Y0 P1 - Y1 P0: eight products, two reductions
+template <>
+MB_HD Fp2 madd_y3<Fp2>(const Fp2& R, const Fp2& T, const Fp2& Y1, const Fp2& PPP) {
+    const Fp nR1 = Fp::neg(R.c1), nY0 = Fp::neg(Y1.c0), nY1 = Fp::neg(Y1.c1);
+    return {Fp::sop4_inline(R.c0, T.c0, nR1, T.c1, nY0, PPP.c0, Y1.c1, PPP.c1),
+            Fp::sop4_inline(R.c0, T.c1, R.c1, T.c0, nY0, PPP.c1, nY1, PPP.c0)};
+}
+#endif
 #endif
 
 // acc += (affine q), q optionally negated

@@ -317,6 +317,50 @@ struct Mont {
         for (int i = 0; i < N; ++i) s.v[i] = borrow ? s.v[i] : t.v[i];
         return s;
     }
+    // the same with four products (Fp2: both components of R T - Y PPP): the running value stays below
+    // 5p (2^32 + 1) < 0.51 * 2^(32 (N + 1)), the result below (4 p^2 + 2^(32N) p) / 2^(32N) < 1.41 p
+    MB_HD static Mont sop4_inline(const Mont& a0, const Mont& b0, const Mont& a1, const Mont& b1, const Mont& a2,
+                                  const Mont& b2, const Mont& a3, const Mont& b3) {
+        uint32_t ev[N], od[N];
+        MB_UNROLL
+        for (int j = 0; j < N; j += 2) {
+            ev[j] = mul_lo(a0.v[j], b0.v[0]);
+            ev[j + 1] = mul_hi(a0.v[j], b0.v[0]);
+            od[j] = mul_lo(a0.v[j + 1], b0.v[0]);
+            od[j + 1] = mul_hi(a0.v[j + 1], b0.v[0]);
+        }
+        row_acc(ev, od, a1.v, b1.v[0]);
+        row_acc(ev, od, a2.v, b2.v[0]);
+        row_acc(ev, od, a3.v, b3.v[0]);
+        row_redc(ev, od);
+        MB_UNROLL
+        for (int i = 1; i < N; i += 2) {
+            row_shift_acc(od, ev, a0.v, b0.v[i]);
+            row_acc(od, ev, a1.v, b1.v[i]);
+            row_acc(od, ev, a2.v, b2.v[i]);
+            row_acc(od, ev, a3.v, b3.v[i]);
+            row_redc(od, ev);
+            if (i + 1 < N) {
+                row_shift_acc(ev, od, a0.v, b0.v[i + 1]);
+                row_acc(ev, od, a1.v, b1.v[i + 1]);
+                row_acc(ev, od, a2.v, b2.v[i + 1]);
+                row_acc(ev, od, a3.v, b3.v[i + 1]);
+                row_redc(ev, od);
+            }
+        }
+        Mont s, t;
+        s.v[0] = add_cc(ev[0], od[1]);
+        MB_UNROLL
+        for (int i = 1; i < N - 1; ++i) s.v[i] = addc_cc(ev[i], od[i + 1]);
+        s.v[N - 1] = addc(ev[N - 1], 0);
+        t.v[0] = sub_cc(s.v[0], C::mod(0));
+        MB_UNROLL
+        for (int i = 1; i < N; ++i) t.v[i] = subc_cc(s.v[i], C::mod(i));
+        uint32_t borrow = subc(0, 0);
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) s.v[i] = borrow ? s.v[i] : t.v[i];
+        return s;
+    }
     // (A dedicated squaring -- cross products once, product-scanning reduction, 222 instead of 288
     // wide multiplies -- is exact but measured 2 % SLOWER inside the accumulation kernel: its
     // three-word column accumulator serialises what the row-wise form leaves independent.
@@ -423,6 +467,11 @@ struct Fp2 {
     MB_HD static Fp2 neg(const Fp2& a) { return {Fp::neg(a.c0), Fp::neg(a.c1)}; }
     MB_HD static Fp2 dbl(const Fp2& a) { return {Fp::dbl(a.c0), Fp::dbl(a.c1)}; }
     MB_HD static Fp2 mul(const Fp2& a, const Fp2& b) {
+#if defined(MB_FP2_SOP) && !defined(MB_COLD_MUL)
+        // same 864 wide multiplies as Karatsuba's three multiplications, as two fused two-product reductions
+        Fp na1 = Fp::neg(a.c1);
+        return {Fp::sop2_inline(a.c0, b.c0, na1, b.c1), Fp::sop2_inline(a.c0, b.c1, a.c1, b.c0)};
+#endif
         Fp t0 = Fp::mul(a.c0, b.c0);
         Fp t1 = Fp::mul(a.c1, b.c1);
         Fp t2 = Fp::mul(Fp::add(a.c0, a.c1), Fp::add(b.c0, b.c1));
