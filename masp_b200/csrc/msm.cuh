@@ -349,7 +349,7 @@ void launch_scan(const ScanArgs& a, cudaStream_t s) {
 // Tasks are handed to threads in descending length (a counting sort), so the
 // 32 lanes of a warp run equal trip counts and the long tasks start first.
 // ---------------------------------------------------------------------------
-static const uint32_t SEG_LEN = 128;
+static const uint32_t SEG_LEN = 128;  // 256: same rate; 64: -4 % (profiles/r02_ab_ntt_block_and_segments.jsonl)
 static const uint32_t ORDER_CAP = SEG_LEN + 1;
 struct SegArgs {
     size_t nthreads;          // buckets

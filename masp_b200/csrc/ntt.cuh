@@ -241,7 +241,7 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
         f.k3 = d.k2;
         f.group = 0;
         f.L = NTT_SMEM_L1;
-        f.logC = 11 - f.L;
+        f.logC = NTT_SMEM_LOG_ELEMS - f.L;
         f.nblocks = (size_t)batch * ((n >> f.L) >> f.logC);
         f.src = src;
         f.src_stride = src_stride;
@@ -254,7 +254,7 @@ inline void ntt_run(const NttDomain& d, const NttPlan& p, uint32_t batch, const 
         launch_ntt_fused(f, s);
         f.group = 1;
         f.L = d.log_n - NTT_SMEM_L1;
-        f.logC = 11 - f.L;
+        f.logC = NTT_SMEM_LOG_ELEMS - f.L;
         f.nblocks = (size_t)batch * ((n >> f.L) >> f.logC);
         f.src = tmp0;
         f.src_stride = n;

@@ -45,7 +45,10 @@ struct NttFusedArgs {
     Fr k2, k3;
 };
 
-static const uint32_t NTT_SMEM_ELEMS = 2048, NTT_SMEM_THREADS = 256, NTT_SMEM_L1 = 9;
+// 2048 scalars per block, 2 blocks per SM.  1024 (128 threads, 4 blocks per SM at the same 128 registers)
+// measured 554 against 559 Spend proofs/s (profiles/r02_ab_ntt_block_and_segments.jsonl).
+static const uint32_t NTT_SMEM_LOG_ELEMS = 11, NTT_SMEM_ELEMS = 1u << NTT_SMEM_LOG_ELEMS,
+                      NTT_SMEM_THREADS = NTT_SMEM_ELEMS / 8, NTT_SMEM_L1 = 9;
 // arrays sit Ln + 1 elements apart: consecutive arrays start 8 banks apart, so the gather / scatter phases
 // (consecutive threads -> consecutive arrays) do not pile onto one bank group; at most 2048 / 8 arrays
 static const uint32_t NTT_SMEM_ALLOC = NTT_SMEM_ELEMS + NTT_SMEM_ELEMS / 8;
@@ -244,7 +247,7 @@ void launch_ntt_fused(const NttFusedArgs& a, cudaStream_t);
 #endif
 #else
 #ifdef MB_DEFINE_NTT
-__global__ void __launch_bounds__(NTT_SMEM_THREADS, 2) ntt_fused(const NttFusedArgs a) {
+__global__ void __launch_bounds__(NTT_SMEM_THREADS, 512 / NTT_SMEM_THREADS) ntt_fused(const NttFusedArgs a) {
     extern __shared__ __align__(128) unsigned char ntt_fused_smem[];
     Fr regs[1][8];
     ntt_fused_block(a, blockIdx.x, reinterpret_cast<Fr*>(ntt_fused_smem), regs);
