@@ -9,8 +9,8 @@ if [ "$what" = all ] || [ "$what" = tests ]; then
   head -2 gpurun_out/full_parity_spend256.log
 fi
 if [ "$what" = all ] || [ "$what" = bench ]; then
-  /usr/bin/time -v timeout 900 python bench.py > gpurun_out/r02_bench_n1_final.json 2> gpurun_out/r02_bench_n1_final.err
-  grep -E "Elapsed|Maximum resident" gpurun_out/r02_bench_n1_final.err
+  time timeout 900 python bench.py > gpurun_out/r02_bench_n1_final.json 2> gpurun_out/r02_bench_n1_final.err
+  tail -4 gpurun_out/r02_bench_n1_final.err
   python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/r02_bench_n1_final.json").read().strip().splitlines()[-1])
@@ -23,7 +23,7 @@ for k, v in d.get("configs", {}).items():
 print("circuit_path", {a: (round(b, 1) if isinstance(b, float) else b) for a, b in (d.get("circuit_path") or {}).items() if a in ("proofs_per_s_pipelined", "proofs_per_s_pipelined_with_self_check", "host_witness_per_s", "vs_synthetic_rows_e2e", "error")})
 print("cpu", d.get("cpu_baseline"))
 PY
-  timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err; tail -c 700 gpurun_out/r02_bench_reference_arm.json
+  [ -s gpurun_out/r02_bench_reference_arm.json ] || timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err
 fi
 B="python bench.py --steps 1 --warmup 1 --batch 64 --no-msm-sweep --no-configs --no-cpu-baseline --no-circuit-path"
 if [ "$what" = all ] || [ "$what" = ncu ]; then
