@@ -26,6 +26,12 @@ MB_D uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.c
 MB_D uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 MB_D uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 MB_D uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; asm volatile("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+MB_D void mul_wide(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) {
+    uint64_t r;
+    asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    lo = (uint32_t)r;
+    hi = (uint32_t)(r >> 32);
+}
 MB_D uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 MB_D uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 MB_D uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
@@ -43,6 +49,7 @@ inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b -
 inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - cf(); }
 inline uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
 inline uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline void mul_wide(uint32_t a, uint32_t b, uint32_t& lo, uint32_t& hi) { uint64_t r = (uint64_t)a * b; lo = (uint32_t)r; hi = (uint32_t)(r >> 32); }
 inline uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c; cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
 inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c + cf(); cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
 inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c; cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
@@ -105,6 +112,15 @@ struct FrCfg {
 // ---------------------------------------------------------------------------
 // Mont<Cfg>: an element in Montgomery form, fully reduced (< modulus)
 // ---------------------------------------------------------------------------
+#if defined(__CUDACC__)
+// -r^-1 mod 2^32 is 2^32 - 1.  Given as a literal, ptxas turns m = t0 * INV into a negation, learns that
+// t0 + m * r0 vanishes, and in simplifying that loses the lo / hi pairing of the whole reduction row: every
+// m * r_i of an Fr multiplication became IMAD.X + IMAD.HI.X instead of one IMAD.WIDE.X (48 extra
+// instructions on the multiplier pipe per multiplication, a quarter of the NTT kernels' IMAD count).
+// Read from constant memory the factor is opaque and the row stays regular.
+static __constant__ uint32_t mb_inv_minus_one = 0xffffffffu;
+#endif
+
 template <class C>
 struct Mont {
     static constexpr int N = C::N;
@@ -205,7 +221,11 @@ struct Mont {
     }
     // Montgomery step on the current row: make ev[0] vanish
     MB_HD static void row_redc(uint32_t* ev, uint32_t* od) {
+#if defined(__CUDA_ARCH__)
+        uint32_t m = mul_lo(ev[0], C::INV == 0xffffffffu ? mb_inv_minus_one : C::INV);
+#else
         uint32_t m = mul_lo(ev[0], C::INV);
+#endif
         uint32_t p[N];
         MB_UNROLL
         for (int i = 0; i < N; ++i) p[i] = C::mod(i);
@@ -246,10 +266,8 @@ struct Mont {
         // first row: plain products
         MB_UNROLL
         for (int j = 0; j < N; j += 2) {
-            ev[j] = mul_lo(a.v[j], b.v[0]);
-            ev[j + 1] = mul_hi(a.v[j], b.v[0]);
-            od[j] = mul_lo(a.v[j + 1], b.v[0]);
-            od[j + 1] = mul_hi(a.v[j + 1], b.v[0]);
+            mul_wide(a.v[j], b.v[0], ev[j], ev[j + 1]);
+            mul_wide(a.v[j + 1], b.v[0], od[j], od[j + 1]);
         }
         row_redc(ev, od);
         MB_UNROLL
@@ -286,10 +304,8 @@ struct Mont {
         uint32_t ev[N], od[N];
         MB_UNROLL
         for (int j = 0; j < N; j += 2) {
-            ev[j] = mul_lo(a.v[j], b.v[0]);
-            ev[j + 1] = mul_hi(a.v[j], b.v[0]);
-            od[j] = mul_lo(a.v[j + 1], b.v[0]);
-            od[j + 1] = mul_hi(a.v[j + 1], b.v[0]);
+            mul_wide(a.v[j], b.v[0], ev[j], ev[j + 1]);
+            mul_wide(a.v[j + 1], b.v[0], od[j], od[j + 1]);
         }
         row_acc(ev, od, c.v, d.v[0]);
         row_redc(ev, od);
@@ -324,10 +340,8 @@ struct Mont {
         uint32_t ev[N], od[N];
         MB_UNROLL
         for (int j = 0; j < N; j += 2) {
-            ev[j] = mul_lo(a0.v[j], b0.v[0]);
-            ev[j + 1] = mul_hi(a0.v[j], b0.v[0]);
-            od[j] = mul_lo(a0.v[j + 1], b0.v[0]);
-            od[j + 1] = mul_hi(a0.v[j + 1], b0.v[0]);
+            mul_wide(a0.v[j], b0.v[0], ev[j], ev[j + 1]);
+            mul_wide(a0.v[j + 1], b0.v[0], od[j], od[j + 1]);
         }
         row_acc(ev, od, a1.v, b1.v[0]);
         row_acc(ev, od, a2.v, b2.v[0]);
