@@ -297,10 +297,13 @@ struct Mont {
     }
     // r = (a * b + c * d) * 2^(-32N) mod p: both products share one accumulator pair and ONE Montgomery
     // reduction (N rows of N wide multiplies saved against two multiplications and an addition).
-    // Bounds: the running value stays below 3p (2^32 + 1) < 2^(32 (N + 1)) -- the pair holds N + 1 limbs and
-    // 3p < 0.31 * 2^(32N) for both moduli used here -- and the result below (2 p^2 + 2^(32N) p) / 2^(32N)
-    // < 1.21 p, so one conditional subtraction brings it under p.
+    // Bounds: the running value stays below 3p (2^32 + 1), which the pair's N + 1 limbs hold when
+    // 3p < 2^(32N): true for Fp (p = 0.10 * 2^384), NOT for Fr (r = 0.45 * 2^256), hence SOP2_OK; the
+    // result is below (2 p^2 + 2^(32N) p) / 2^(32N) < 1.21 p, so one conditional subtraction brings it under p.
+    static constexpr bool SOP2_OK = C::mod(N - 1) < 0x55555555u;  // 3p < 2^(32N)
+    static constexpr bool SOP4_OK = C::mod(N - 1) < 0x33333333u;  // 5p < 2^(32N)
     MB_HD static Mont sop2_inline(const Mont& a, const Mont& b, const Mont& c, const Mont& d) {
+        static_assert(SOP2_OK, "modulus too close to 2^(32N) for a fused two-product reduction");
         uint32_t ev[N], od[N];
         MB_UNROLL
         for (int j = 0; j < N; j += 2) {
@@ -337,6 +340,7 @@ struct Mont {
     // 5p (2^32 + 1) < 0.51 * 2^(32 (N + 1)), the result below (4 p^2 + 2^(32N) p) / 2^(32N) < 1.41 p
     MB_HD static Mont sop4_inline(const Mont& a0, const Mont& b0, const Mont& a1, const Mont& b1, const Mont& a2,
                                   const Mont& b2, const Mont& a3, const Mont& b3) {
+        static_assert(SOP4_OK, "modulus too close to 2^(32N) for a fused four-product reduction");
         uint32_t ev[N], od[N];
         MB_UNROLL
         for (int j = 0; j < N; j += 2) {

@@ -45,11 +45,16 @@ MB_HD uint32_t st_field(uint64_t key, size_t tid) {
     if (!F::add(a, F::neg(a)).is_zero()) bad++;
     if (!F::mul(F::add(a, b), a).eq(F::add(F::mul_portable(a, a), F::mul_portable(b, a)))) bad++;
     if (!F::to_std(F::from_std(a)).eq(a)) bad++;
-    // fused a b + c d against two multiplications and an addition, the extreme case (p-1)^2 + (p-1)^2 included
-    F c = st_rand<F>(key ^ 0x9e37, 2 * tid), d = st_rand<F>(key ^ 0x9e37, 2 * tid + 1);
-    if (tid % 7 == 0) c = F::sub(F::zero(), F::one());
-    if (tid % 35 == 0) { b = a; d = c; }  // a = b = c = d = p - 1 on both cycles
-    if (!F::sop2_inline(a, b, c, d).eq(F::add(F::mul_portable(a, b), F::mul_portable(c, d)))) bad++;
+    // fused a b + c d (+ ...) against separate multiplications and additions, the extreme case
+    // (p-1)^2 + (p-1)^2 (+ ...) included; only where the modulus leaves the head-room (Fp)
+    if constexpr (F::SOP4_OK) {
+        F c = st_rand<F>(key ^ 0x9e37, 2 * tid), d = st_rand<F>(key ^ 0x9e37, 2 * tid + 1);
+        if (tid % 7 == 0) c = F::sub(F::zero(), F::one());
+        if (tid % 35 == 0) { b = a; d = c; }  // a = b = c = d = p - 1 on both cycles
+        if (!F::sop2_inline(a, b, c, d).eq(F::add(F::mul_portable(a, b), F::mul_portable(c, d)))) bad++;
+        if (!F::sop4_inline(a, b, c, d, b, c, d, a).eq(F::add(F::add(F::mul_portable(a, b), F::mul_portable(c, d)),
+                                                             F::add(F::mul_portable(b, c), F::mul_portable(d, a))))) bad++;
+    }
     return bad;
 }
 MB_HD void selftest_body(const SelfTestArgs& a, size_t tid) {
