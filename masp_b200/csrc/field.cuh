@@ -447,8 +447,76 @@ struct Mont {
         return subc(0, 0) != 0;
     }
 
-    // a^(p-2) by square-and-multiply over the bits of p - 2
+    // a^-1 by the binary extended Euclidean algorithm on the plain integers (u, v) = (a R mod p, p) with
+    // cofactors (x1, x2): ~2 * 32 N rounds of a shift or a subtraction on N limbs, against the Fermat power's
+    // ~1.5 * 32 N dependent multiplications of N^2 wide multiplies each -- this chain is what a caller of
+    // `proof_finish` / `sum_partials` (one thread per point) waits for.  The loop yields (a R)^-1 as a plain
+    // integer; one multiplication by R^3 turns it into a^-1 R.  inv(0) = 0, like the power.
     MB_HD static Mont inv(const Mont& a) {
+        if (a.is_zero()) return zero();
+        Mont u = a, v, x1 = zero(), x2 = zero();
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) v.v[i] = C::mod(i);
+        x1.v[0] = 1;
+        MB_NOUNROLL
+        for (;;) {
+            MB_NOUNROLL
+            while ((u.v[0] & 1u) == 0) {
+                shr1(u, 0);
+                halve(x1);
+            }
+            if (is_plain_one(u)) break;
+            MB_NOUNROLL
+            while ((v.v[0] & 1u) == 0) {
+                shr1(v, 0);
+                halve(x2);
+            }
+            if (is_plain_one(v)) break;
+            if (plain_geq(u, v)) {
+                plain_sub(u, v);
+                x1 = sub(x1, x2);
+            } else {
+                plain_sub(v, u);
+                x2 = sub(x2, x1);
+            }
+        }
+        const Mont r3 = mul(r2(), r2());
+        return mul(is_plain_one(u) ? x1 : x2, r3);
+    }
+    MB_HD static bool is_plain_one(const Mont& a) {
+        uint32_t o = a.v[0] ^ 1u;
+        MB_UNROLL
+        for (int i = 1; i < N; ++i) o |= a.v[i];
+        return o == 0;
+    }
+    MB_HD static void shr1(Mont& a, uint32_t top_bit) {  // a = (top_bit : a) >> 1
+        MB_UNROLL
+        for (int i = 0; i < N - 1; ++i) a.v[i] = (a.v[i] >> 1) | (a.v[i + 1] << 31);
+        a.v[N - 1] = (a.v[N - 1] >> 1) | (top_bit << 31);
+    }
+    MB_HD static void halve(Mont& x) {  // x / 2 mod p for x < p (x + p < 2^(32N) for both moduli: no carry out)
+        if (x.v[0] & 1u) {
+            x.v[0] = add_cc(x.v[0], C::mod(0));
+            MB_UNROLL
+            for (int i = 1; i < N - 1; ++i) x.v[i] = addc_cc(x.v[i], C::mod(i));
+            x.v[N - 1] = addc(x.v[N - 1], C::mod(N - 1));
+        }
+        shr1(x, 0);
+    }
+    MB_HD static bool plain_geq(const Mont& a, const Mont& b) {
+        sub_cc(a.v[0], b.v[0]);
+        MB_UNROLL
+        for (int i = 1; i < N; ++i) subc_cc(a.v[i], b.v[i]);
+        return subc(0, 0) == 0;
+    }
+    MB_HD static void plain_sub(Mont& a, const Mont& b) {  // a -= b, a >= b
+        a.v[0] = sub_cc(a.v[0], b.v[0]);
+        MB_UNROLL
+        for (int i = 1; i < N - 1; ++i) a.v[i] = subc_cc(a.v[i], b.v[i]);
+        a.v[N - 1] = subc(a.v[N - 1], b.v[N - 1]);
+    }
+    // a^(p-2) by square-and-multiply over the bits of p - 2 (the self-test's reference for inv)
+    MB_HD static Mont inv_fermat(const Mont& a) {
         uint32_t e[N];
         uint32_t borrow = 2;
         for (int i = 0; i < N; ++i) {

@@ -45,6 +45,17 @@ MB_HD uint32_t st_field(uint64_t key, size_t tid) {
     if (!F::add(a, F::neg(a)).is_zero()) bad++;
     if (!F::mul(F::add(a, b), a).eq(F::add(F::mul_portable(a, a), F::mul_portable(b, a)))) bad++;
     if (!F::to_std(F::from_std(a)).eq(a)) bad++;
+    // binary-Euclid inverse against the Fermat power (a few threads: the power is ~570 multiplications),
+    // and a * a^-1 = 1 everywhere; 1, 2, p - 1 and 0 among the operands
+    {
+        F x = a;
+        if (tid % 11 == 1) x = F::one();
+        if (tid % 11 == 2) x = F::dbl(F::one());
+        if (tid % 11 == 3) x = F::zero();
+        F xi = F::inv(x);
+        if (x.is_zero() ? !xi.is_zero() : !F::mul(x, xi).eq(F::one())) bad++;
+        if (tid < 24 && !xi.eq(F::inv_fermat(x))) bad++;
+    }
     // fused a b + c d (+ ...) against separate multiplications and additions, the extreme case
     // (p-1)^2 + (p-1)^2 (+ ...) included; only where the modulus leaves the head-room (Fp)
     if constexpr (F::SOP4_OK) {

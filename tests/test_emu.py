@@ -146,6 +146,23 @@ def test_local_tx_prover_surface(emu, oracle):
         assert out.raw == hashlib.blake2b(blob[:n], digest_size=64).digest(), n
 
 
+@pytest.mark.parametrize("c", [5, 13, 15, 16, 17])
+def test_msm_window_sizes_and_the_scalar_fold(emu, oracle, c, monkeypatch):
+    """Every window size the library may pick, including 15 and 17 (where folding s > (r - 1) / 2 to r - s saves
+    a window: 254 bits in 17 / 15 windows): scalars on both sides of the fold, at the window boundaries, with the
+    largest top digit, and the values whose folded image lands in the "ones" buckets."""
+    monkeypatch.setenv("MB200_C_MSM", str(c))
+    R = syn.R_INT
+    H = (R - 1) // 2
+    scalars = [H, H + 1, H - 1, H + 2, R - 1, R - 2, 2, 1, 0, (1 << 254) - 1, 1 << 254, R - (1 << 200), (1 << c) - 1,
+               1 << (c - 1), (1 << (c - 1)) + 1, H - (1 << (c - 1)), H >> 3, R - ((1 << c) - 1), (1 << (2 * c)) - 1]
+    scalars += [int(x) for x in rand_scalars(13, 1000 + c)]
+    n = len(scalars)
+    logs = syn.fr_uniform(syn.MASTER_SEED, 12, n)
+    bases = oracle.g1_gen_mul(syn.limbs_to_bytes(logs), n)
+    assert emu.msm_g1(bases, ib(scalars), n) == oracle.msm_g1(bases, ib(scalars), n)
+
+
 def test_msm_special_bases(emu, oracle):
     """Repeated bases (P + P), negated pairs (P + (-P)), identities: the XYZZ accumulator
     must take the tangent, drop the cancelling pair and pass infinities through."""
