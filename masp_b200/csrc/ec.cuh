@@ -262,10 +262,7 @@ MB_HD void glv_split(const uint32_t* k, uint32_t rem[4], uint32_t q[4]) {
         q[j] = qq[j];  // k < r < lambda^2 + ..., so the quotient fits 128 bits (checked by the caller's tests)
     }
 }
-// INL: the doublings inlined (units with inlined multiplications only): ptxas overlaps the independent
-// multiplications of one doubling, which is what the 128-doubling chain of `proof_cmul` waits for
-template <bool INL>
-MB_HD XYZZ<Fp> xyzz_mul_glv_t(const XYZZ<Fp>& p, const uint32_t* k) {
+MB_COLD XYZZ<Fp> xyzz_mul_glv(const XYZZ<Fp>& p, const uint32_t* k) {
     uint32_t k1[4], k2[4];
     glv_split(k, k1, k2);
     XYZZ<Fp> tab[16];
@@ -281,7 +278,7 @@ MB_HD XYZZ<Fp> xyzz_mul_glv_t(const XYZZ<Fp>& p, const uint32_t* k) {
     MB_NOUNROLL
     for (int w = 31; w >= 0; --w) {
         MB_NOUNROLL
-        for (int d = 0; d < 4; ++d) acc = INL ? xyzz_dbl(acc) : xyzz_dbl_cold(acc);
+        for (int d = 0; d < 4; ++d) acc = xyzz_dbl_cold(acc);
         uint32_t d1 = (k1[w >> 3] >> ((w & 7) * 4)) & 15u, d2 = (k2[w >> 3] >> ((w & 7) * 4)) & 15u;
         if (d1) xyzz_add_cold(acc, tab[d1]);
         if (d2) {
@@ -292,7 +289,6 @@ MB_HD XYZZ<Fp> xyzz_mul_glv_t(const XYZZ<Fp>& p, const uint32_t* k) {
     }
     return acc;
 }
-MB_COLD XYZZ<Fp> xyzz_mul_glv(const XYZZ<Fp>& p, const uint32_t* k) { return xyzz_mul_glv_t<false>(p, k); }
 
 typedef Affine<Fp> G1Affine;
 typedef Affine<Fp2> G2Affine;

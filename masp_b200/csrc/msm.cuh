@@ -642,25 +642,6 @@ MB_HD void horner_g2_body(const HornerArgs<Fp2>& a, size_t tid) { horner_body<Fp
 MB_K_MSM_G1(msm_horner_g1, HornerArgs<Fp>, horner_g1_body, 32)
 MB_K_MSM_G2(msm_horner_g2, HornerArgs<Fp2>, horner_g2_body, 32)
 
-// s * A and r * B1 (two threads per proof); defined in the unit with inlined multiplications: the chain of
-// 128 doublings is the longest single item of a lone proof's latency
-struct CmulArgs {
-    size_t nthreads;  // 2 * proofs
-    const G1XYZZ* a_res;
-    const G1XYZZ* b1_res;
-    const uint32_t* pool;
-    size_t pool_stride, r_index, s_index;
-    G1XYZZ* out;  // [proofs][2]
-};
-MB_HD void cmul_body(const CmulArgs& a, size_t tid) {
-    size_t proof = tid >> 1;
-    const uint32_t* base = a.pool + proof * a.pool_stride * 8;
-    if (tid & 1) a.out[tid] = xyzz_mul_glv_t<true>(a.b1_res[proof], base + a.r_index * 8);
-    else a.out[tid] = xyzz_mul_glv_t<true>(a.a_res[proof], base + a.s_index * 8);
-}
-MB_K_MSM_G1(proof_cmul, CmulArgs, cmul_body, 32)
-
-
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
@@ -915,9 +896,7 @@ void msm_reduce_buckets(const MsmClass& k, uint32_t n_inst, XYZZ<F>* out, MsmScr
         w.lp[flip].ensure(ra.nthreads * sizeof(XYZZ<F>));
         ra.Xo = w.lx[flip].as<XYZZ<F>>();
         ra.Po = w.lp[flip].as<XYZZ<F>>();
-        // no tables = a standalone MSM, a handful of instances = a wallet proving one transaction: the caller
-        // waits for exactly this chain, so take the inlined additions; batches keep the small out-of-line form
-        launch_red<F>(ra, s, !k.precomp || n_inst <= 8);
+        launch_red<F>(ra, s, !k.precomp);  // no tables = a standalone MSM: its caller waits for this chain
         X = ra.Xo;
         P = ra.Po;
         n_w = ra.n_out;

@@ -97,6 +97,23 @@ MB_HD void fill_one_body(const FillOneArgs& a, size_t tid) {
 }
 MB_K_G1(pool_fill_one, FillOneArgs, fill_one_body, 64)
 
+// s * A and r * B1 (two threads per proof)
+struct CmulArgs {
+    size_t nthreads;  // 2 * proofs
+    const G1XYZZ* a_res;
+    const G1XYZZ* b1_res;
+    const uint32_t* pool;
+    size_t pool_stride, r_index, s_index;
+    G1XYZZ* out;  // [proofs][2]
+};
+MB_HD void cmul_body(const CmulArgs& a, size_t tid) {
+    size_t proof = tid >> 1;
+    const uint32_t* base = a.pool + proof * a.pool_stride * 8;
+    if (tid & 1) a.out[tid] = xyzz_mul_glv(a.b1_res[proof], base + a.r_index * 8);
+    else a.out[tid] = xyzz_mul_glv(a.a_res[proof], base + a.s_index * 8);
+}
+MB_K_G1(proof_cmul, CmulArgs, cmul_body, 32)
+
 // affine + compressed encoding of the three proof points (three threads per proof)
 struct FinishArgs {
     size_t nthreads;  // 3 * proofs
