@@ -290,6 +290,30 @@ def circuit_path(pv, key, shape, n, rounds, seed=20261017, torch=None, threads=0
     }
 
 
+def integer_roof(shape, c_hl, c_a, fpmul, proofs_per_s_per_gpu):
+    """The bound that binds: Fp-multiplication equivalents per proof against the live
+    multiplication rate of the chip.  Counts for this bench's witnesses (boolean aux are 0 or 1 with equal
+    probability: 0 costs nothing, 1 one mixed addition; a full-width scalar one addition per window):
+    G1 mixed addition = 10 products + 9 Montgomery reductions = 9.5 multiplications, G2 = 36 + 18 half
+    units = 27, an Fr multiplication 128 / 276 of an Fp one; six transforms of m log2(m) / 2 butterflies."""
+    nwin = lambda c: -(-254 // c)          # windows after folding s > (r - 1) / 2 (msm.cuh msm_nwin)
+    sh = shape
+    full_l = sh.n_aux - sh.n_bool
+    full_a = sh.full_ab + sh.full_a
+    full_b = sh.full_ab + sh.full_b
+    bool_a = sh.bool_ab + sh.bool_a
+    bool_b = sh.bool_ab + sh.bool_b
+    g1 = (sh.h_len + full_l) * nwin(c_hl) + sh.n_bool / 2 + (full_a + full_b) * nwin(c_a) + (bool_a + bool_b) / 2
+    g2 = full_b * nwin(c_a) + bool_b / 2
+    fr = 6 * sh.m * sh.log_m / 2
+    muls = 9.5 * g1 + 27.0 * g2 + fr * 128.0 / 276.0
+    roof = fpmul / muls if muls else 0.0
+    return {"fp_mul_equivalents_per_proof": muls, "g1_additions_per_proof": g1, "g2_additions_per_proof": g2,
+            "fr_multiplications_per_proof": fr, "proofs_per_s_at_measured_fp_mul_rate": roof,
+            "frac": (proofs_per_s_per_gpu / roof) if roof else None,
+            "note": "bucket reductions, scalar multiplications of the assembly and to-affine conversions (< 4 %) not counted"}
+
+
 def run_reference(args):
     """The reference's own CPU implementation of the path, restated
     (oracle/c: window-parallel Pippenger + radix-2 domain on all host cores;
@@ -697,6 +721,7 @@ def main():
             "note": "this path is bound by 32-bit integer multiply-add issue, not HBM (SURVEY.md §7/§8d): "
                     "see fp_mul_per_s for the integer-side figure",
             "fp_mul_per_s": fpmul,
+            "integer_roof": integer_roof(shape, params.window_hl, params.window_a, fpmul, value / n_gpus),
             "whole_proof_hbm_frac": shape.algorithmic_bytes() * value / n_gpus / 1e9 / peak,
         },
     }
