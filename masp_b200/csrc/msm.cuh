@@ -6,14 +6,20 @@
 // masp_proofs/src/sapling/prover.rs:116-117, 201-202, 251-252).
 //
 // Schedule (B200-first, not the reference's window-per-task loop):
-//   1. msm_count    one thread per (instance, base): signed c-bit digits of the
-//                   scalar -> histogram over buckets.  0 is skipped; 1 goes to
-//                   a spread set of "ones" buckets (the reference's 0/1 fast
+//   1. msm_count    one thread per (instance, base): the scalar is folded to
+//                   min(s, r - s) (sign carried by the entries), cut into signed
+//                   c-bit digits -> histogram over buckets.  0 is skipped; 1 goes
+//                   to a spread set of "ones" buckets (the reference's 0/1 fast
 //                   path) so no bucket is a hot spot.
-//   2. scan         exclusive prefix sum of the histogram.
+//   2. scan         exclusive prefix sum of the histogram (block-cooperative tiles).
 //   3. msm_scatter  same walk, writes (table index, sign) entries bucket-sorted.
-//   4. msm_accumulate  one thread per bucket: XYZZ accumulator in registers,
-//                   affine table points gathered from HBM/L2, 8M+2S mixed add.
+//   3b. seg / order buckets are cut into segments of <= 128 entries (tasks), tasks
+//                   are counting-sorted longest first.
+//   4. msm_accumulate  one thread per task: XYZZ accumulator in registers, affine
+//                   table points gathered from HBM/L2, mixed add with 10 products
+//                   and 9 Montgomery reductions (ec.cuh madd_y3); a bucket with a
+//                   single segment is written directly, split ones are folded by
+//                   msm_combine_round (tree of fan-in 8).
 //   5. reduce       sum_b b * S_b by chunked running sums, a few levels.
 // With a precomputed table (2^(c w) * B_k for every window w, built once at
 // key load and resident in HBM) all windows of an instance share ONE bucket
