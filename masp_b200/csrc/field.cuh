@@ -383,7 +383,89 @@ struct Mont {
     // wide multiplies -- is exact but measured 2 % SLOWER inside the accumulation kernel: its
     // three-word column accumulator serialises what the row-wise form leaves independent.
     // Kept with its test under scripts/microbench/sqr_ps.cuh.)
+    // Row-wise triangular squaring (MB_TRI_SQR units): a^2 = sum_i a_i B^i * (a_i B^i + 2 sum_{j>i} a_j B^j),
+    // B = 2^32.  Row i multiplies a_i into the vector (a_i, 2 U_i), U_i = the limbs above i, whose doubled
+    // limbs are e_{i+1} = a_{i+1} << 1 and d_j = (a_j << 1) | (a_{j-1} >> 31) above that (a < 2^(32N - 1) for
+    // both moduli, so nothing is shifted out).  Every contribution to limb k comes from a row <= k, so the
+    // interleaved Montgomery steps see the same low limbs as in mul(a, a) and the result is bit-identical; row i
+    // simply has no products below position i: 78 instead of 144 product multiplies for N = 12, on the same
+    // two accumulators (the skipped pairs of the odd chain become carry-propagating moves on the ALU pipe).
+    // Row k brings its doubled cross terms in ahead of the rows that would add them in mul(a, a), so the running
+    // value is bounded by 2a + p < 3p instead of 2p: the same head-room condition as sop2 (Fp yes, Fr no).
+    MB_HD static void row_shift_acc_tri(uint32_t* ev, uint32_t* od, const uint32_t* x, uint32_t y, int j0) {
+        ev[0] = add_cc(ev[0], od[1]);
+        MB_UNROLL
+        for (int j = 0; j < N - 2; j += 2) {
+            if (j + 1 >= j0) {
+                od[j] = madc_lo_cc(x[j + 1], y, od[j + 2]);
+                od[j + 1] = madc_hi_cc(x[j + 1], y, od[j + 3]);
+            } else {
+                od[j] = addc_cc(od[j + 2], 0);
+                od[j + 1] = addc_cc(od[j + 3], 0);
+            }
+        }
+        od[N - 2] = madc_lo_cc(x[N - 1], y, 0);
+        od[N - 1] = madc_hi(x[N - 1], y, 0);
+        bool first = true;
+        MB_UNROLL
+        for (int j = 0; j < N; j += 2) {
+            if (j >= j0) {
+                ev[j] = first ? mad_lo_cc(x[j], y, ev[j]) : madc_lo_cc(x[j], y, ev[j]);
+                ev[j + 1] = madc_hi_cc(x[j], y, ev[j + 1]);
+                first = false;
+            }
+        }
+        if (!first) od[N - 1] = addc(od[N - 1], 0);  // the even chain's carry (no even term at all for j0 = N - 1)
+    }
+    MB_HD static Mont sqr_inline(const Mont& a) {
+        static_assert(SOP2_OK, "modulus too close to 2^(32N) for the triangular squaring");
+        uint32_t d[N], ev[N], od[N], x[N];
+        d[0] = a.v[0] << 1;
+        MB_UNROLL
+        for (int j = 1; j < N; ++j) d[j] = (a.v[j] << 1) | (a.v[j - 1] >> 31);
+        // row 0: a_0 * (a_0, e_1, d_2, ...)
+        MB_UNROLL
+        for (int j = 0; j < N; ++j) x[j] = j == 0 ? a.v[0] : (j == 1 ? (a.v[1] << 1) : d[j]);
+        MB_UNROLL
+        for (int j = 0; j < N; j += 2) {
+            mul_wide(x[j], a.v[0], ev[j], ev[j + 1]);
+            mul_wide(x[j + 1], a.v[0], od[j], od[j + 1]);
+        }
+        row_redc(ev, od);
+        MB_UNROLL
+        for (int i = 1; i < N; i += 2) {
+            MB_UNROLL
+            for (int j = 0; j < N; ++j) x[j] = j == i ? a.v[j] : (j == i + 1 ? (a.v[j] << 1) : d[j]);
+            row_shift_acc_tri(od, ev, x, a.v[i], i);
+            row_redc(od, ev);
+            if (i + 1 < N) {
+                MB_UNROLL
+                for (int j = 0; j < N; ++j) x[j] = j == i + 1 ? a.v[j] : (j == i + 2 ? (a.v[j] << 1) : d[j]);
+                row_shift_acc_tri(ev, od, x, a.v[i + 1], i + 1);
+                row_redc(ev, od);
+            }
+        }
+        Mont s, t;
+        s.v[0] = add_cc(ev[0], od[1]);
+        MB_UNROLL
+        for (int i = 1; i < N - 1; ++i) s.v[i] = addc_cc(ev[i], od[i + 1]);
+        s.v[N - 1] = addc(ev[N - 1], 0);
+        t.v[0] = sub_cc(s.v[0], C::mod(0));
+        MB_UNROLL
+        for (int i = 1; i < N; ++i) t.v[i] = subc_cc(s.v[i], C::mod(i));
+        uint32_t borrow = subc(0, 0);
+        MB_UNROLL
+        for (int i = 0; i < N; ++i) s.v[i] = borrow ? s.v[i] : t.v[i];
+        return s;
+    }
+#if defined(MB_TRI_SQR) && !defined(MB_COLD_MUL)
+    MB_HD static Mont sqr(const Mont& a) {
+        if constexpr (SOP2_OK) return sqr_inline(a);
+        else return mul(a, a);
+    }
+#else
     MB_HD static Mont sqr(const Mont& a) { return mul(a, a); }
+#endif
 
     // reference multiplication with 64-bit temporaries (self-test only)
     MB_HD static Mont mul_portable(const Mont& a, const Mont& b) {

@@ -59,6 +59,8 @@ MB_HD uint32_t st_field(uint64_t key, size_t tid) {
     // fused a b + c d (+ ...) against separate multiplications and additions, the extreme case
     // (p-1)^2 + (p-1)^2 (+ ...) included; only where the modulus leaves the head-room (Fp)
     if constexpr (F::SOP4_OK) {
+        if (!F::sqr_inline(a).eq(F::mul_portable(a, a))) bad++;  // the triangular squaring of the accumulate kernels
+        if (!F::sqr_inline(b).eq(F::mul_portable(b, b))) bad++;
         F c = st_rand<F>(key ^ 0x9e37, 2 * tid), d = st_rand<F>(key ^ 0x9e37, 2 * tid + 1);
         if (tid % 7 == 0) c = F::sub(F::zero(), F::one());
         if (tid % 35 == 0) { b = a; d = c; }  // a = b = c = d = p - 1 on both cycles
