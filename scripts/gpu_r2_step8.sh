@@ -1,5 +1,6 @@
 #!/bin/bash
 # Round 2, eighth GPU call: G2 accumulate variants as alternate libraries (scripts/debug/abl/lib_g2_*.so):
+# (the alternate libraries under scripts/debug/abl were built ad hoc for this one call -- the shipped sources with one macro or constant changed -- and are not kept; the outcomes are in profiles/r02_ab_*.jsonl)
 #   A Karatsuba Fp2 (shipped)  B Fp2 mul as two fused two-product reductions  C = B + Y3 as two four-product reductions  D = A + that Y3
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out

@@ -1,5 +1,6 @@
 #!/bin/bash
 # Round 2, ninth GPU call: alternate libraries (scripts/debug/abl): fused NTT on 1024-element blocks (4 per SM),
+# (the alternate libraries under scripts/debug/abl were built ad hoc for this one call -- the shipped sources with one macro or constant changed -- and are not kept; the outcomes are in profiles/r02_ab_*.jsonl)
 # accumulate segments of 256 / 64 entries; the shipped library first and last.
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
